@@ -1,0 +1,174 @@
+/* rpgo_b200.h — C ABI of the B200-native PCM outlier-rejection hot path.
+ *
+ * This is the drop-in boundary for the one data-parallel path of MIT-SPARK/Kimera-RPGO that this
+ * library rebuilds: the three calls Pcm<poseT,T>::removeOutliers makes into arithmetic —
+ *   updateOdom            (reference include/KimeraRPGO/outlier/Pcm.h:516-557)   -> rpgo_odom_append
+ *   isOdomConsistent +
+ *   incrementAdjMatrix    (Pcm.h:604-629, :725-768, via parseAndIncrementAdjMatrix :414-502)
+ *                                                                                 -> rpgo_lc_append
+ *   findMaxCliqueHeu / findMaxCliqueHeuIncremental / findMaxClique
+ *                         (src/utils/GraphUtils.cpp:9-44, called from Pcm.h:865, :922, :328)
+ *                                                                                 -> rpgo_find_inliers
+ *   removeLastLoopClosure's matrix shrink (Pcm.h:320-323)                         -> rpgo_lc_remove_last
+ * Factor classification, shared_ptr bookkeeping and output-graph assembly stay on the host in the
+ * OutlierRemoval subclass that calls this ABI.
+ *
+ * Conventions: plain C types only; all pointers are HOST pointers to caller-owned buffers unless a
+ * name ends in _device; device memory is owned by the library; every function returns an int status
+ * (RPGO_OK == 0) and never throws; a handle is single-threaded (one CUDA stream, one GPU).
+ * There is no CPU fallback: rpgo_create fails with RPGO_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Data layout:
+ *   key        uint64, gtsam::Key (gtsam::Symbol: chr = key >> 56, index = low 56 bits)
+ *   pose  3D   12 doubles: R row-major (9) then t (3)          2D   4 doubles: cos, sin, x, y
+ *   cov   3D   6x6 row-major, GTSAM tangent order [rot; trans]  2D   3x3 row-major, (x, y, theta)
+ *         (== noiseModel::Gaussian::covariance() of the factor; a NaN rotation block selects the
+ *          reference's rotation_info=false path, GeometryUtils.h:98-113)
+ *   adjacency  bitset, row i = 64-bit little-endian words, bit j of row i <=> closures i and j of the
+ *              group are pairwise consistent; symmetric, zero diagonal (Pcm.h:756-763)
+ */
+#ifndef RPGO_B200_H_
+#define RPGO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RPGO_OK 0
+#define RPGO_ERR_INVALID 1   /* bad argument */
+#define RPGO_ERR_CUDA 2      /* CUDA runtime error / no device */
+#define RPGO_ERR_NOMEM 3
+#define RPGO_ERR_NOT_FOUND 4 /* unknown group / key */
+
+#define RPGO_MODE_PCM 0      /* Pcm2D / Pcm3D: Mahalanobis distance  (Pcm.h:1167-1168) */
+#define RPGO_MODE_SIMPLE 1   /* PcmSimple2D / PcmSimple3D: average trans/rot per node (Pcm.h:1169-1170) */
+
+#define RPGO_CLIQUE_HEU 0              /* findMaxCliqueHeu            GraphUtils.cpp:19-27 */
+#define RPGO_CLIQUE_HEU_INCREMENTAL 1  /* findMaxCliqueHeuIncremental GraphUtils.cpp:30-44 */
+#define RPGO_CLIQUE_EXACT 2            /* findMaxClique               GraphUtils.cpp:9-17  */
+
+#define RPGO_TRAJ_FOLD 0  /* strict left fold, bit-identical to the reference's order (Pcm.h:553) */
+#define RPGO_TRAJ_SCAN 1  /* chunked parallel prefix scan (re-associated; deterministic) */
+
+#define RPGO_KERNEL_AUTO 0
+#define RPGO_KERNEL_DIRECT 1  /* v0: one thread per pair, operands gathered from global memory */
+#define RPGO_KERNEL_TILED 2   /* TMA-staged shared-memory tiles */
+
+typedef struct rpgo_handle rpgo_handle;
+
+/* Mirrors KimeraRPGO::PcmParams (reference include/KimeraRPGO/SolverParams.h:33-56). A threshold < 0
+ * disables the corresponding check exactly as Pcm.h:74-82 does. */
+typedef struct rpgo_cfg {
+  int32_t dim;   /* 2 or 3 */
+  int32_t mode;  /* RPGO_MODE_* */
+  double odom_threshold;
+  double lc_threshold;
+  double odom_trans_threshold;
+  double odom_rot_threshold;
+  double dist_trans_threshold;
+  double dist_rot_threshold;
+  int32_t incremental; /* PcmParams::incremental (informational; the caller picks the clique mode) */
+  int32_t device;      /* CUDA ordinal, -1 = current device */
+  int32_t traj_mode;   /* RPGO_TRAJ_* */
+  int32_t kernel;      /* RPGO_KERNEL_* for the pairwise kernel */
+  int32_t rank;        /* multi-GPU: this handle computes row chunks {rank, 2*world-1-rank} of every group */
+  int32_t world;       /* 1 = single GPU */
+  double band;         /* near-threshold flag half width; <= 0 selects 1e-9 */
+  int32_t scan_chunk;  /* RPGO_TRAJ_SCAN chunk length; <= 0 selects 64 */
+  int32_t reserved;
+} rpgo_cfg;
+
+int rpgo_default_cfg(rpgo_cfg* cfg);
+int rpgo_create(const rpgo_cfg* cfg, rpgo_handle** out);
+void rpgo_destroy(rpgo_handle* h);
+const char* rpgo_last_error(const rpgo_handle* h);
+/* block until all work queued on the handle's stream has finished */
+int rpgo_sync(rpgo_handle* h);
+/* the handle's cudaStream_t (as an opaque pointer), for event timing and collectives issued by the caller */
+void* rpgo_stream(rpgo_handle* h);
+
+/* ---- K1: odometry trajectory cache (Pcm::updateOdom, Pcm.h:516-557) --------------------------
+ * Appends n odometry factors in arrival order: poses[new_key] = poses[prev_key].compose(T(delta)).
+ * init_pose (n poses, may be NULL = identity) is consulted only for a factor that introduces a new
+ * prefix: it is values.at(prev_key), which seeds the trajectory with zero covariance (:534-542). */
+int rpgo_odom_append(rpgo_handle* h, int64_t n, const uint64_t* prev_key, const uint64_t* new_key,
+                     const double* delta_pose, const double* delta_cov, const double* init_pose);
+
+/* parity / debug: cumulative entry of `key` (cov may be NULL; node/rot_info may be NULL) */
+int rpgo_traj_get(rpgo_handle* h, uint64_t key, double* pose, double* cov, int32_t* node, int32_t* rot_info);
+int64_t rpgo_traj_size(rpgo_handle* h);
+
+/* ---- K2 + K3: loop closures (Pcm::parseAndIncrementAdjMatrix for pose-pose closures, :456-494) -
+ * For each of the n closures in arrival order: intra-robot closures are checked against odometry
+ * (isOdomConsistent; rejected ones are dropped and not counted); accepted closures join the group of
+ * their unordered prefix pair (ObservationId, TypeUtils.h:44-58) and the group's adjacency is extended by
+ * one row/column per closure (incrementAdjMatrix).
+ * Outputs (each may be NULL): accepted[i] 0/1; group[i] group ordinal (first-seen order) or -1;
+ * index[i] position inside the group or -1; odom_dist[i] the odometry-check distance (NaN if not run). */
+int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const uint64_t* key_to,
+                   const double* pose, const double* cov, uint8_t* accepted, int32_t* group, int32_t* index,
+                   double* odom_dist);
+
+int32_t rpgo_num_groups(rpgo_handle* h);
+/* prefixes (id1 <= id2) and number of stored closures of group g */
+int rpgo_group_info(rpgo_handle* h, int32_t g, uint8_t* id1, uint8_t* id2, int64_t* n);
+/* group ordinal of the unordered prefix pair, or -1 */
+int32_t rpgo_find_group(rpgo_handle* h, uint8_t id1, uint8_t id2);
+
+/* Pcm::removeLastLoopClosure's data part (Pcm.h:314-323): drop the last closure of group g (last row and
+ * column of its adjacency). key_from/key_to receive the removed edge. RPGO_ERR_NOT_FOUND if empty. */
+int rpgo_lc_remove_last(rpgo_handle* h, int32_t g, uint64_t* key_from, uint64_t* key_to);
+
+/* ---- K4 / K5: inlier selection ------------------------------------------------------------------
+ * Runs the reference's clique finder on group g's adjacency.  ids_out (capacity >= group size) receives
+ * exactly what Pcm.h:865-869 consumes: the first *size_out entries of the vector the reference returns —
+ * for the heuristic modes that is FMC's scratch buffer (findCliqueHeu.cpp:110-113), reproduced verbatim,
+ * which is generally not the greedy clique itself; true_clique_out (may be NULL, same capacity)
+ * receives the vertices the greedy chain actually selected.
+ * HEU_INCREMENTAL: candidates are the last n_new closures, bound starts at prev_size; *size_out = 0 when
+ * the clique did not grow (caller keeps its previous inliers, Pcm.h:929-939). */
+int rpgo_find_inliers(rpgo_handle* h, int32_t g, int32_t clique_mode, int64_t n_new, int64_t prev_size,
+                      int32_t* ids_out, int64_t* size_out, int32_t* true_clique_out);
+
+/* ---- parity / inspection ---------------------------------------------------------------------- */
+/* copy group g's adjacency to the host: n rows of stride_words 64-bit words (stride_words >= ceil(n/64)) */
+int rpgo_adj_bits(rpgo_handle* h, int32_t g, uint64_t* rows_out, int64_t stride_words);
+/* device view of the same bitset (valid until the next call that grows the group) */
+int rpgo_adj_bits_device(rpgo_handle* h, int32_t g, void** bits_device, int64_t* stride_words, int64_t* n);
+/* vertex degrees (popcount of each row) */
+int rpgo_degrees(rpgo_handle* h, int32_t g, int32_t* deg_out);
+/* pairs (i, j), i < j, whose distance lies within cfg.band of the threshold (the explicitly flagged
+ * near-threshold set).  pairs_out holds up to cap pairs as 2 ints each; *n_out = total flagged. */
+int rpgo_near_threshold(rpgo_handle* h, int32_t g, int32_t* pairs_out, int64_t cap, int64_t* n_out);
+/* debug: recompute distances of all pairs of group g into an n x n row-major host matrix (small n only) */
+int rpgo_pair_distances(rpgo_handle* h, int32_t g, double* dist_out);
+
+/* ---- measurement hooks --------------------------------------------------------------------------
+ * Re-run the pairwise kernel over columns [j_begin, n) of group g from the device-resident tables
+ * (inputs already in HBM; same launch rpgo_lc_append issues).  Used by bench.py for kernel-only timing. */
+int rpgo_group_recompute(rpgo_handle* h, int32_t g, int64_t j_begin);
+/* multi-GPU: after the caller has all-gathered the upper-triangle row chunks, rebuild the lower
+ * triangle and the degrees on this GPU */
+int rpgo_group_finalize(rpgo_handle* h, int32_t g);
+/* row-chunk geometry of group g for the all-gather: rows are cut into 2*world chunks of chunk_rows rows */
+int rpgo_group_chunking(rpgo_handle* h, int32_t g, int64_t* chunk_rows, int64_t* padded_rows);
+/* number of kernels this handle has launched since creation */
+int64_t rpgo_launch_count(rpgo_handle* h);
+/* FP64 FMA micro-benchmark used as the roofline denominator: returns achieved DFMA TFLOP/s */
+int rpgo_fp64_peak(int32_t device, double* tflops_out);
+
+/* test / benchmark hook: create (or replace) the group of prefix pair (id1, id2) with n vertices and the
+ * given symmetric adjacency (n rows of stride_words 64-bit words) without running the pairwise kernel,
+ * so that the clique kernels can be exercised on arbitrary graphs. */
+int rpgo_debug_load_group(rpgo_handle* h, uint8_t id1, uint8_t id2, int64_t n, const uint64_t* rows,
+                          int64_t stride_words, int32_t* group_out);
+
+const char* rpgo_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RPGO_B200_H_ */

@@ -1,0 +1,894 @@
+/* capi.cu — host-side state and the C ABI (include/rpgo_b200.h) of the B200 PCM path.
+ *
+ * Host logic restated here (reference file:line):
+ *   trajectory bookkeeping of Pcm::updateOdom                        Pcm.h:516-557
+ *   per-closure flow of Pcm::parseAndIncrementAdjMatrix              Pcm.h:456-494
+ *   ObservationId grouping                                            TypeUtils.h:44-58, Pcm.h:472-486
+ *   std::map::operator[] default-entry semantics of Trajectory       GraphUtils.h:40-42
+ *   removeLastLoopClosure's matrix shrink                             Pcm.h:314-323
+ * All arithmetic runs in the CUDA kernels (pcm_kernels.cu, pcm_tiled.cu, clique_kernels.cu); there
+ * is no host fallback.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <set>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/rpgo_b200.h"
+#include "kernels.cuh"
+
+using namespace rpgo;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  /* grow to at least `bytes`; optionally keep the first `keep` bytes; new memory is zeroed */
+  cudaError_t ensure(size_t bytes, size_t keep, cudaStream_t st) {
+    if (bytes <= cap) return cudaSuccess;
+    size_t ncap = std::max(bytes, cap * 2);
+    ncap = (ncap + 255) & ~size_t(255);
+    void* np = nullptr;
+    cudaError_t e = cudaMalloc(&np, ncap);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(np, 0, ncap, st);
+    if (e != cudaSuccess) return e;
+    if (p && keep) {
+      e = cudaMemcpyAsync(np, p, std::min(keep, cap), cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) return e;
+    }
+    if (p) {
+      cudaStreamSynchronize(st);
+      cudaFree(p);
+    }
+    p = np;
+    cap = ncap;
+    return cudaSuccess;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  ~PinBuf() { if (p) cudaFreeHost(p); }
+  void* ensure(size_t bytes) {
+    if (bytes <= cap) return p;
+    if (p) cudaFreeHost(p);
+    cap = std::max(bytes, cap * 2);
+    if (cudaMallocHost(&p, cap) != cudaSuccess) { p = nullptr; cap = 0; }
+    return p;
+  }
+};
+
+struct Group {
+  uint8_t id1 = 0, id2 = 0;
+  int64_t n = 0;         /* closures stored */
+  int64_t cap = 0;       /* capacity in closures (multiple of 128) */
+  int64_t stride32 = 0;  /* adjacency row stride in 32-bit words (= cap / 32) */
+  DevBuf lc, idxf, idxb, pfx, bits, deg, fl_pairs, fl_count;
+  std::vector<uint64_t> kfrom, kto;
+  std::vector<int32_t> h_idxf, h_idxb;
+  std::vector<uint8_t> h_pfx;
+};
+
+constexpr int64_t FLAG_CAP = 1 << 20;
+
+}  // namespace
+
+struct rpgo_handle {
+  rpgo_cfg cfg;
+  int dim = 3, mode = 0, E = 50, PS = 12, NN = 36;
+  bool odom_check = true, loop_check = true;
+  Thresholds th;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+
+  /* trajectory table: entry 0 is the default-constructed T (identity, zero covariance, node 0) */
+  DevBuf traj;
+  int64_t traj_n = 0;
+  std::unordered_map<uint64_t, int32_t> key2idx;
+  std::set<uint8_t> prefixes; /* prefixes for which odom_trajectories_ has an entry */
+
+  std::vector<Group*> groups;
+  std::map<std::pair<uint8_t, uint8_t>, int32_t> gindex;
+
+  /* staging */
+  PinBuf pin;
+  DevBuf d_stage;
+  DevBuf d_lcent, d_ok, d_dist;
+  /* clique scratch */
+  DevBuf c_degmask, c_picks, c_elim, c_result, c_ctl, c_rwork;
+
+  ~rpgo_handle() {
+    for (Group* g : groups) delete g;
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+#define H_CHECK_CUDA(h, x)                                                           \
+  do {                                                                               \
+    cudaError_t e_ = (x);                                                            \
+    if (e_ != cudaSuccess) {                                                         \
+      (h)->err = std::string(#x) + ": " + cudaGetErrorString(e_);                    \
+      return RPGO_ERR_CUDA;                                                          \
+    }                                                                                \
+  } while (0)
+
+static inline uint8_t key_chr(uint64_t k) { return (uint8_t)(k >> 56); }
+
+static int traj_lookup(rpgo_handle* h, uint64_t key) {
+  auto it = h->key2idx.find(key);
+  return it == h->key2idx.end() ? 0 : it->second; /* missing key -> default entry (operator[] semantics) */
+}
+
+static int ensure_traj(rpgo_handle* h, int64_t entries) {
+  H_CHECK_CUDA(h, h->traj.ensure((size_t)entries * h->E * sizeof(double), (size_t)h->traj_n * h->E * sizeof(double), h->stream));
+  return RPGO_OK;
+}
+
+static GroupView group_view(rpgo_handle* h, Group* g) {
+  GroupView v;
+  v.lc = g->lc.as<double>();
+  v.idx_front = g->idxf.as<int32_t>();
+  v.idx_back = g->idxb.as<int32_t>();
+  v.pfx_front = g->pfx.as<uint8_t>();
+  v.bits = g->bits.as<uint32_t>();
+  v.stride32 = g->stride32;
+  v.deg = g->deg.as<int32_t>();
+  v.n = (int32_t)g->n;
+  return v;
+}
+
+static Shard group_shard(rpgo_handle* h, Group* g) {
+  Shard s;
+  s.rank = h->cfg.rank;
+  s.world = h->cfg.world < 1 ? 1 : h->cfg.world;
+  int64_t c = (g->n + 2 * s.world - 1) / (2 * s.world);
+  c = (c + 31) / 32 * 32;
+  s.chunk_rows = c < 32 ? 32 : c;
+  return s;
+}
+
+/* grow a group's device arrays to hold `need` closures */
+static int ensure_group(rpgo_handle* h, Group* g, int64_t need) {
+  if (need <= g->cap) return RPGO_OK;
+  int64_t ncap = std::max<int64_t>(need, g->cap * 2);
+  ncap = (ncap + 127) / 128 * 128;
+  cudaStream_t st = h->stream;
+  H_CHECK_CUDA(h, g->lc.ensure((size_t)ncap * h->E * sizeof(double), (size_t)g->n * h->E * sizeof(double), st));
+  H_CHECK_CUDA(h, g->idxf.ensure((size_t)ncap * 4, (size_t)g->n * 4, st));
+  H_CHECK_CUDA(h, g->idxb.ensure((size_t)ncap * 4, (size_t)g->n * 4, st));
+  H_CHECK_CUDA(h, g->pfx.ensure((size_t)ncap, (size_t)g->n, st));
+  H_CHECK_CUDA(h, g->deg.ensure((size_t)ncap * 4, 0, st));
+  if (h->loop_check) {
+    /* adjacency: ncap rows x ncap/32 words; the row pitch changes, so copy row by row (2D copy) */
+    const int64_t nstride = ncap / 32;
+    /* in multi-GPU mode rows are padded to 2*world chunks */
+    const int64_t rows = ncap + 64 * (int64_t)std::max(1, h->cfg.world);
+    void* nb = nullptr;
+    const size_t bytes = (size_t)rows * nstride * 4;
+    H_CHECK_CUDA(h, cudaMalloc(&nb, bytes));
+    H_CHECK_CUDA(h, cudaMemsetAsync(nb, 0, bytes, st));
+    if (g->bits.p && g->n > 0)
+      H_CHECK_CUDA(h, cudaMemcpy2DAsync(nb, (size_t)nstride * 4, g->bits.p, (size_t)g->stride32 * 4,
+                                        (size_t)((g->n + 31) / 32) * 4, (size_t)g->n, cudaMemcpyDeviceToDevice, st));
+    if (g->bits.p) {
+      H_CHECK_CUDA(h, cudaStreamSynchronize(st));
+      cudaFree(g->bits.p);
+    }
+    g->bits.p = nb;
+    g->bits.cap = bytes;
+    g->stride32 = nstride;
+    if (!g->fl_pairs.p) {
+      H_CHECK_CUDA(h, g->fl_pairs.ensure((size_t)FLAG_CAP * 2 * 4, 0, st));
+      H_CHECK_CUDA(h, g->fl_count.ensure(8, 0, st));
+    }
+  }
+  g->cap = ncap;
+  return RPGO_OK;
+}
+
+static Flagged group_flagged(Group* g) {
+  Flagged f;
+  f.pairs = g->fl_pairs.as<int32_t>();
+  f.count = g->fl_count.as<unsigned long long>();
+  f.cap = FLAG_CAP;
+  return f;
+}
+
+static int run_pairwise(rpgo_handle* h, Group* g, int64_t j_begin, double* dist_dev) {
+  if (!h->loop_check || g->n < 2) return RPGO_OK;
+  GroupView v = group_view(h, g);
+  Shard sh = group_shard(h, g);
+  int kernel = h->cfg.kernel;
+  if (dist_dev) kernel = RPGO_KERNEL_DIRECT;
+  if (kernel == RPGO_KERNEL_AUTO) kernel = RPGO_KERNEL_DIRECT;
+  if (kernel == RPGO_KERNEL_TILED && !(h->dim == 3 && h->mode == MODE_PCM)) kernel = RPGO_KERNEL_DIRECT;
+  if (kernel == RPGO_KERNEL_TILED)
+    launch_pairwise_tiled(h->dim, h->mode, v, h->traj.as<double>(), (int)j_begin, sh, h->th, group_flagged(g), h->stream);
+  else
+    launch_pairwise_direct(h->dim, h->mode, v, h->traj.as<double>(), (int)j_begin, sh, h->th, group_flagged(g), dist_dev,
+                           h->stream);
+  h->launches += 1;
+  H_CHECK_CUDA(h, cudaGetLastError());
+  return RPGO_OK;
+}
+
+static int finalize_group(rpgo_handle* h, Group* g, int64_t j_begin) {
+  if (!h->loop_check || g->n < 1) return RPGO_OK;
+  launch_mirror(g->bits.as<uint32_t>(), g->stride32, (int)g->n, (int)j_begin, h->stream);
+  launch_degree(g->bits.as<uint32_t>(), g->stride32, (int)g->n, g->deg.as<int32_t>(), h->stream);
+  h->launches += 2;
+  H_CHECK_CUDA(h, cudaGetLastError());
+  return RPGO_OK;
+}
+
+extern "C" {
+
+const char* rpgo_version(void) { return "rpgo_b200 0.1 (sm_100a)"; }
+
+int rpgo_default_cfg(rpgo_cfg* c) {
+  if (!c) return RPGO_ERR_INVALID;
+  memset(c, 0, sizeof(*c));
+  c->dim = 3;
+  c->mode = RPGO_MODE_PCM;
+  /* PcmParams defaults, SolverParams.h:35-42 */
+  c->odom_threshold = 10.0;
+  c->lc_threshold = 5.0;
+  c->odom_trans_threshold = 0.05;
+  c->odom_rot_threshold = 0.005;
+  c->dist_trans_threshold = 0.01;
+  c->dist_rot_threshold = 0.001;
+  c->incremental = 0;
+  c->device = -1;
+  c->traj_mode = RPGO_TRAJ_FOLD;
+  c->kernel = RPGO_KERNEL_AUTO;
+  c->rank = 0;
+  c->world = 1;
+  c->band = 1e-9;
+  c->scan_chunk = 64;
+  return RPGO_OK;
+}
+
+int rpgo_create(const rpgo_cfg* cfg, rpgo_handle** out) {
+  if (!cfg || !out) return RPGO_ERR_INVALID;
+  if ((cfg->dim != 2 && cfg->dim != 3) || (cfg->mode != 0 && cfg->mode != 1)) return RPGO_ERR_INVALID;
+  if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return RPGO_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return RPGO_ERR_CUDA; /* no CPU fallback */
+  if (cfg->device >= 0) {
+    if (cfg->device >= ndev) return RPGO_ERR_INVALID;
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return RPGO_ERR_CUDA;
+  }
+  rpgo_handle* h = new rpgo_handle();
+  h->cfg = *cfg;
+  if (h->cfg.band <= 0) h->cfg.band = 1e-9;
+  if (h->cfg.scan_chunk <= 0) h->cfg.scan_chunk = 64;
+  h->dim = cfg->dim;
+  h->mode = cfg->mode;
+  h->E = cfg->dim == 3 ? Dim<3>::ENTRY : Dim<2>::ENTRY;
+  h->PS = cfg->dim == 3 ? 12 : 4;
+  h->NN = cfg->dim == 3 ? 36 : 9;
+  /* Pcm.h:74-82 */
+  h->odom_check = !(cfg->odom_threshold < 0 || cfg->odom_rot_threshold < 0 || cfg->odom_trans_threshold < 0);
+  h->loop_check = !(cfg->lc_threshold < 0 || cfg->dist_rot_threshold < 0 || cfg->dist_trans_threshold < 0);
+  h->th.odom = cfg->odom_threshold;
+  h->th.lc = cfg->lc_threshold;
+  h->th.odom_trans = cfg->odom_trans_threshold;
+  h->th.odom_rot = cfg->odom_rot_threshold;
+  h->th.dist_trans = cfg->dist_trans_threshold;
+  h->th.dist_rot = cfg->dist_rot_threshold;
+  h->th.band = h->cfg.band;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return RPGO_ERR_CUDA;
+  }
+  /* entry 0 = default T: identity pose, zero covariance, node 0, rotation_info true */
+  if (h->traj.ensure((size_t)1024 * h->E * sizeof(double), 0, h->stream) != cudaSuccess) {
+    delete h;
+    return RPGO_ERR_CUDA;
+  }
+  std::vector<double> e0(h->E, 0.0);
+  if (h->dim == 3) { e0[0] = e0[4] = e0[8] = 1.0; e0[Dim<3>::OFF_ROT] = 1.0; }
+  else { e0[0] = 1.0; e0[Dim<2>::OFF_ROT] = 1.0; }
+  cudaMemcpyAsync(h->traj.p, e0.data(), sizeof(double) * h->E, cudaMemcpyHostToDevice, h->stream);
+  cudaStreamSynchronize(h->stream);
+  h->traj_n = 1;
+  *out = h;
+  return RPGO_OK;
+}
+
+void rpgo_destroy(rpgo_handle* h) {
+  if (!h) return;
+  cudaStreamSynchronize(h->stream);
+  delete h;
+}
+
+const char* rpgo_last_error(const rpgo_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int rpgo_sync(rpgo_handle* h) {
+  if (!h) return RPGO_ERR_INVALID;
+  H_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+  return RPGO_OK;
+}
+
+void* rpgo_stream(rpgo_handle* h) { return h ? (void*)h->stream : nullptr; }
+int64_t rpgo_launch_count(rpgo_handle* h) { return h ? h->launches : 0; }
+int64_t rpgo_traj_size(rpgo_handle* h) { return h ? (int64_t)h->key2idx.size() : 0; }
+
+/* ---------------------------------------------------------------------------------------------- */
+int rpgo_odom_append(rpgo_handle* h, int64_t n, const uint64_t* prev_key, const uint64_t* new_key,
+                     const double* delta_pose, const double* delta_cov, const double* init_pose) {
+  if (!h || n < 0) return RPGO_ERR_INVALID;
+  if (n == 0) return RPGO_OK;
+  if (!prev_key || !new_key || !delta_pose || !delta_cov) return RPGO_ERR_INVALID;
+  const int E = h->E, PS = h->PS, NN = h->NN;
+  cudaStream_t st = h->stream;
+
+  /* host pass: resolve indices, seed new prefixes, build chains (Pcm.h:524-556) */
+  struct Step { int32_t src; int32_t out; int64_t k; };
+  std::vector<std::vector<Step>> chains;       /* steps per chain */
+  std::vector<int32_t> chain_start;            /* start entry per chain */
+  std::unordered_map<uint8_t, int> open_chain; /* prefix -> chain index whose tail can be extended */
+  std::unordered_map<int, uint64_t> chain_tail_key;
+  std::set<int32_t> produced;                  /* entries written by this batch */
+  std::vector<std::pair<int32_t, int64_t>> seeds; /* (entry, step k) */
+  int64_t new_entries = h->traj_n;
+  bool need_flush_order = false;
+
+  for (int64_t k = 0; k < n; ++k) {
+    const uint8_t prefix = key_chr(new_key[k]);
+    if (h->prefixes.find(prefix) == h->prefixes.end()) {
+      /* new prefix: poses[prev_key] = (values.at(prev_key), zero cov)  Pcm.h:534-542 */
+      h->prefixes.insert(prefix);
+      int32_t idx;
+      auto it = h->key2idx.find(prev_key[k]);
+      if (it == h->key2idx.end()) {
+        idx = (int32_t)new_entries++;
+        h->key2idx[prev_key[k]] = idx;
+      } else {
+        idx = it->second;
+      }
+      seeds.push_back({idx, k});
+    }
+    const int32_t src = traj_lookup(h, prev_key[k]);
+    int32_t out;
+    auto it = h->key2idx.find(new_key[k]);
+    if (it == h->key2idx.end()) {
+      out = (int32_t)new_entries++;
+      h->key2idx[new_key[k]] = out;
+    } else {
+      out = it->second;
+    }
+    auto oc = open_chain.find(prefix);
+    if (oc != open_chain.end() && chain_tail_key[oc->second] == prev_key[k]) {
+      chains[oc->second].push_back({src, out, k});
+      chain_tail_key[oc->second] = new_key[k];
+    } else {
+      if (produced.count(src)) need_flush_order = true; /* starts from an entry another chain writes */
+      chains.push_back({{src, out, k}});
+      chain_start.push_back(src);
+      open_chain[prefix] = (int)chains.size() - 1;
+      chain_tail_key[(int)chains.size() - 1] = new_key[k];
+    }
+    produced.insert(out);
+  }
+  int rc = ensure_traj(h, new_entries);
+  if (rc != RPGO_OK) return rc;
+
+  /* seeds: host-built entries, uploaded before any kernel */
+  if (!seeds.empty()) {
+    std::vector<double> e((size_t)E, 0.0);
+    for (auto& s : seeds) {
+      std::fill(e.begin(), e.end(), 0.0);
+      if (init_pose) {
+        memcpy(e.data(), init_pose + (size_t)s.second * PS, sizeof(double) * PS);
+      } else {
+        if (h->dim == 3) { e[0] = e[4] = e[8] = 1.0; } else { e[0] = 1.0; }
+      }
+      e[h->dim == 3 ? Dim<3>::OFF_ROT : Dim<2>::OFF_ROT] = 1.0;
+      H_CHECK_CUDA(h, cudaMemcpyAsync(h->traj.as<double>() + (size_t)s.first * E, e.data(), sizeof(double) * E,
+                                      cudaMemcpyHostToDevice, st));
+      H_CHECK_CUDA(h, cudaStreamSynchronize(st)); /* e is reused */
+    }
+  }
+
+  /* flatten chains; steps of one chain are contiguous */
+  const size_t bytes_pose = (size_t)n * PS * 8, bytes_cov = (size_t)n * NN * 8;
+  const size_t off_cov = bytes_pose, off_out = off_cov + bytes_cov, off_chain = off_out + (size_t)n * 4;
+  const size_t total = off_chain + chains.size() * sizeof(FoldChain) + 64;
+  char* pin = (char*)h->pin.ensure(total);
+  if (!pin) { h->err = "pinned staging allocation failed"; return RPGO_ERR_NOMEM; }
+  double* p_pose = (double*)pin;
+  double* p_cov = (double*)(pin + off_cov);
+  int32_t* p_out = (int32_t*)(pin + off_out);
+  FoldChain* p_chain = (FoldChain*)(pin + ((off_chain + 15) & ~size_t(15)));
+  int64_t pos = 0;
+  for (size_t c = 0; c < chains.size(); ++c) {
+    p_chain[c].first_step = (int32_t)pos;
+    p_chain[c].n_steps = (int32_t)chains[c].size();
+    p_chain[c].start_idx = chain_start[c];
+    p_chain[c].pad = 0;
+    for (const Step& s : chains[c]) {
+      memcpy(p_pose + (size_t)pos * PS, delta_pose + (size_t)s.k * PS, sizeof(double) * PS);
+      memcpy(p_cov + (size_t)pos * NN, delta_cov + (size_t)s.k * NN, sizeof(double) * NN);
+      p_out[pos] = s.out;
+      ++pos;
+    }
+  }
+  H_CHECK_CUDA(h, h->d_stage.ensure(total, 0, st));
+  H_CHECK_CUDA(h, cudaMemcpyAsync(h->d_stage.p, pin, total, cudaMemcpyHostToDevice, st));
+  char* d = (char*)h->d_stage.p;
+  const double* d_pose = (const double*)d;
+  const double* d_cov = (const double*)(d + off_cov);
+  const int32_t* d_out = (const int32_t*)(d + off_out);
+  const FoldChain* d_chain = (const FoldChain*)(d + ((off_chain + 15) & ~size_t(15)));
+
+  const int nch = (int)chains.size();
+  if (need_flush_order || h->cfg.traj_mode == RPGO_TRAJ_FOLD) {
+    if (need_flush_order) {
+      /* rare: a chain starts from an entry written by an earlier chain of this batch -> serialise */
+      for (int c = 0; c < nch; ++c) {
+        launch_traj_fold(h->dim, h->mode, 1, d_chain + c, d_out, d_pose, d_cov, h->traj.as<double>(), st);
+        h->launches++;
+      }
+    } else {
+      launch_traj_fold(h->dim, h->mode, nch, d_chain, d_out, d_pose, d_cov, h->traj.as<double>(), st);
+      h->launches++;
+    }
+  } else {
+    /* chunked scan */
+    const int chunk = h->cfg.scan_chunk;
+    std::vector<int32_t> chunk_chain, chunk_first, chain_first_chunk(nch), step_chunk((size_t)n);
+    for (int c = 0; c < nch; ++c) {
+      chain_first_chunk[c] = (int32_t)chunk_chain.size();
+      for (int s0 = 0; s0 < p_chain[c].n_steps; s0 += chunk) {
+        const int q = (int)chunk_chain.size();
+        chunk_chain.push_back(c);
+        chunk_first.push_back(p_chain[c].first_step + s0);
+        for (int s = s0; s < std::min(s0 + chunk, p_chain[c].n_steps); ++s) step_chunk[p_chain[c].first_step + s] = q;
+      }
+    }
+    const int total_chunks = (int)chunk_chain.size();
+    const size_t ib = ((size_t)total_chunks * 2 + nch + n) * 4;
+    const size_t ib_al = (ib + 15) & ~size_t(15);
+    static thread_local DevBuf scan_buf;
+    H_CHECK_CUDA(h, scan_buf.ensure(ib_al + (size_t)total_chunks * E * 8, 0, st));
+    std::vector<int32_t> ints;
+    ints.insert(ints.end(), chunk_chain.begin(), chunk_chain.end());
+    ints.insert(ints.end(), chunk_first.begin(), chunk_first.end());
+    ints.insert(ints.end(), chain_first_chunk.begin(), chain_first_chunk.end());
+    ints.insert(ints.end(), step_chunk.begin(), step_chunk.end());
+    H_CHECK_CUDA(h, cudaMemcpyAsync(scan_buf.p, ints.data(), ib, cudaMemcpyHostToDevice, st));
+    H_CHECK_CUDA(h, cudaStreamSynchronize(st));
+    const int32_t* di = scan_buf.as<int32_t>();
+    launch_traj_scan_phases(h->dim, h->mode, nch, d_chain, d_out, d_pose, d_cov, h->traj.as<double>(), chunk, (int)n,
+                            total_chunks, di, di + total_chunks, di + 2 * total_chunks, di + 2 * total_chunks + nch,
+                            (double*)((char*)scan_buf.p + ib_al), st);
+    h->launches += 3;
+  }
+  H_CHECK_CUDA(h, cudaGetLastError());
+  h->traj_n = new_entries;
+  H_CHECK_CUDA(h, cudaStreamSynchronize(st)); /* pinned staging is reused by the next call */
+  return RPGO_OK;
+}
+
+int rpgo_traj_get(rpgo_handle* h, uint64_t key, double* pose, double* cov, int32_t* node, int32_t* rot_info) {
+  if (!h || !pose) return RPGO_ERR_INVALID;
+  auto it = h->key2idx.find(key);
+  if (it == h->key2idx.end()) return RPGO_ERR_NOT_FOUND;
+  std::vector<double> e(h->E);
+  H_CHECK_CUDA(h, cudaMemcpyAsync(e.data(), h->traj.as<double>() + (size_t)it->second * h->E, sizeof(double) * h->E,
+                                  cudaMemcpyDeviceToHost, h->stream));
+  H_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+  memcpy(pose, e.data(), sizeof(double) * h->PS);
+  const int oc = h->dim == 3 ? Dim<3>::OFF_COV : Dim<2>::OFF_COV;
+  const int orr = h->dim == 3 ? Dim<3>::OFF_ROT : Dim<2>::OFF_ROT;
+  const int on = h->dim == 3 ? Dim<3>::OFF_NODE : Dim<2>::OFF_NODE;
+  if (cov) memcpy(cov, e.data() + oc, sizeof(double) * h->NN);
+  if (node) *node = (int32_t)e[on];
+  if (rot_info) *rot_info = e[orr] != 0.0;
+  return RPGO_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const uint64_t* key_to,
+                   const double* pose, const double* cov, uint8_t* accepted, int32_t* group, int32_t* index,
+                   double* odom_dist) {
+  if (!h || n < 0) return RPGO_ERR_INVALID;
+  if (n == 0) return RPGO_OK;
+  if (!key_from || !key_to || !pose || !cov) return RPGO_ERR_INVALID;
+  const int E = h->E, PS = h->PS, NN = h->NN;
+  cudaStream_t st = h->stream;
+
+  /* stage inputs: pose | cov | idxf | idxb | check */
+  const size_t o_cov = (size_t)n * PS * 8, o_if = o_cov + (size_t)n * NN * 8, o_ib = o_if + (size_t)n * 4,
+               o_ck = o_ib + (size_t)n * 4, o_dst = (o_ck + (size_t)n + 15) & ~size_t(15),
+               total = o_dst + (size_t)n * 8;
+  char* pin = (char*)h->pin.ensure(total + (size_t)n * 9 + 64);
+  if (!pin) { h->err = "pinned staging allocation failed"; return RPGO_ERR_NOMEM; }
+  memcpy(pin, pose, (size_t)n * PS * 8);
+  memcpy(pin + o_cov, cov, (size_t)n * NN * 8);
+  int32_t* p_if = (int32_t*)(pin + o_if);
+  int32_t* p_ib = (int32_t*)(pin + o_ib);
+  uint8_t* p_ck = (uint8_t*)(pin + o_ck);
+  uint64_t* p_dst = (uint64_t*)(pin + o_dst);
+  for (int64_t k = 0; k < n; ++k) {
+    const uint8_t cf = key_chr(key_from[k]), cb = key_chr(key_to[k]);
+    const bool intra = cf == cb;
+    p_ck[k] = (intra && h->odom_check) ? 1 : 0;
+    if (p_ck[k]) h->prefixes.insert(cf); /* odom_trajectories_[chr] is created by the lookup, Pcm.h:619 */
+    p_if[k] = traj_lookup(h, key_from[k]);
+    p_ib[k] = traj_lookup(h, key_to[k]);
+  }
+  H_CHECK_CUDA(h, h->d_stage.ensure(total, 0, st));
+  H_CHECK_CUDA(h, h->d_lcent.ensure((size_t)n * E * 8, 0, st));
+  H_CHECK_CUDA(h, h->d_ok.ensure((size_t)n, 0, st));
+  H_CHECK_CUDA(h, h->d_dist.ensure((size_t)n * 8, 0, st));
+  H_CHECK_CUDA(h, cudaMemcpyAsync(h->d_stage.p, pin, o_dst, cudaMemcpyHostToDevice, st));
+  char* d = (char*)h->d_stage.p;
+  launch_lc_prepare(h->dim, h->mode, (int)n, (const double*)d, (const double*)(d + o_cov), (const int32_t*)(d + o_if),
+                    (const int32_t*)(d + o_ib), (const uint8_t*)(d + o_ck), h->traj.as<double>(), h->th,
+                    h->d_lcent.as<double>(), h->d_ok.as<uint8_t>(), h->d_dist.as<double>(), st);
+  h->launches++;
+  H_CHECK_CUDA(h, cudaGetLastError());
+  uint8_t* h_ok = (uint8_t*)(pin + total);
+  double* h_dist = (double*)(pin + ((total + (size_t)n + 15) & ~size_t(15)));
+  /* h_dist region: make sure it is inside the pinned buffer */
+  h_dist = nullptr;
+  std::vector<double> dist_host;
+  H_CHECK_CUDA(h, cudaMemcpyAsync(h_ok, h->d_ok.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+  if (odom_dist) {
+    dist_host.resize((size_t)n);
+    H_CHECK_CUDA(h, cudaMemcpyAsync(dist_host.data(), h->d_dist.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  }
+  H_CHECK_CUDA(h, cudaStreamSynchronize(st));
+  (void)h_dist;
+
+  /* host pass 2: grouping in arrival order (Pcm.h:466-486) */
+  std::map<int32_t, int64_t> old_n; /* groups touched -> size before this call */
+  std::vector<int64_t> need(h->groups.size(), 0);
+  for (int64_t k = 0; k < n; ++k) {
+    if (odom_dist) odom_dist[k] = dist_host[k];
+    if (!h_ok[k]) {
+      if (accepted) accepted[k] = 0;
+      if (group) group[k] = -1;
+      if (index) index[k] = -1;
+      p_dst[k] = 0;
+      continue;
+    }
+    const uint8_t cf = key_chr(key_from[k]), cb = key_chr(key_to[k]);
+    const std::pair<uint8_t, uint8_t> id(std::min(cf, cb), std::max(cf, cb));
+    int32_t gi;
+    auto it = h->gindex.find(id);
+    if (it == h->gindex.end()) {
+      Group* g = new Group();
+      g->id1 = id.first;
+      g->id2 = id.second;
+      gi = (int32_t)h->groups.size();
+      h->groups.push_back(g);
+      h->gindex[id] = gi;
+    } else {
+      gi = it->second;
+    }
+    Group* g = h->groups[gi];
+    if (!old_n.count(gi)) old_n[gi] = g->n;
+    const int64_t idx = g->n++;
+    g->kfrom.push_back(key_from[k]);
+    g->kto.push_back(key_to[k]);
+    g->h_idxf.push_back(p_if[k]);
+    g->h_idxb.push_back(p_ib[k]);
+    g->h_pfx.push_back(cf);
+    if (h->loop_check && idx >= 1) { /* areLoopsConsistent touches both trajectories, Pcm.h:703-710 */
+      h->prefixes.insert(id.first);
+      h->prefixes.insert(id.second);
+    }
+    if (accepted) accepted[k] = 1;
+    if (group) group[k] = gi;
+    if (index) index[k] = (int32_t)idx;
+    p_dst[k] = (uint64_t)idx; /* patched to an address below, once capacities are final */
+    /* remember group in the low bits via a side vector */
+    need.resize(h->groups.size(), 0);
+  }
+  /* capacities (n was advanced above; ensure_group must see the old n for its copies) */
+  for (auto& kv : old_n) {
+    Group* g = h->groups[kv.first];
+    const int64_t n_new = g->n;
+    g->n = kv.second;
+    int rc = ensure_group(h, g, n_new);
+    g->n = n_new;
+    if (rc != RPGO_OK) return rc;
+  }
+  /* destination addresses */
+  {
+    std::map<int32_t, int64_t> cursor = old_n;
+    for (int64_t k = 0; k < n; ++k) {
+      if (!h_ok[k]) continue;
+      const uint8_t cf = key_chr(key_from[k]), cb = key_chr(key_to[k]);
+      const int32_t gi = h->gindex[{std::min(cf, cb), std::max(cf, cb)}];
+      Group* g = h->groups[gi];
+      p_dst[k] = (uint64_t)(uintptr_t)(g->lc.as<double>() + (size_t)(cursor[gi]++) * E);
+    }
+  }
+  H_CHECK_CUDA(h, cudaMemcpyAsync(d + o_dst, p_dst, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  launch_scatter_entries(h->dim, (int)n, h->d_lcent.as<double>(), (const uint64_t*)(d + o_dst), st);
+  h->launches++;
+  for (auto& kv : old_n) {
+    Group* g = h->groups[kv.first];
+    const int64_t o = kv.second, m = g->n - o;
+    H_CHECK_CUDA(h, cudaMemcpyAsync(g->idxf.as<int32_t>() + o, g->h_idxf.data() + o, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+    H_CHECK_CUDA(h, cudaMemcpyAsync(g->idxb.as<int32_t>() + o, g->h_idxb.data() + o, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+    H_CHECK_CUDA(h, cudaMemcpyAsync(g->pfx.as<uint8_t>() + o, g->h_pfx.data() + o, (size_t)m, cudaMemcpyHostToDevice, st));
+  }
+  /* K3 per touched group */
+  for (auto& kv : old_n) {
+    Group* g = h->groups[kv.first];
+    int rc = run_pairwise(h, g, kv.second, nullptr);
+    if (rc != RPGO_OK) return rc;
+    if (h->cfg.world <= 1) {
+      rc = finalize_group(h, g, kv.second);
+      if (rc != RPGO_OK) return rc;
+    }
+  }
+  H_CHECK_CUDA(h, cudaGetLastError());
+  H_CHECK_CUDA(h, cudaStreamSynchronize(st)); /* host vectors / pinned staging are reused */
+  return RPGO_OK;
+}
+
+int32_t rpgo_num_groups(rpgo_handle* h) { return h ? (int32_t)h->groups.size() : 0; }
+
+int rpgo_group_info(rpgo_handle* h, int32_t g, uint8_t* id1, uint8_t* id2, int64_t* n) {
+  if (!h || g < 0 || g >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
+  if (id1) *id1 = h->groups[g]->id1;
+  if (id2) *id2 = h->groups[g]->id2;
+  if (n) *n = h->groups[g]->n;
+  return RPGO_OK;
+}
+
+int32_t rpgo_find_group(rpgo_handle* h, uint8_t id1, uint8_t id2) {
+  if (!h) return -1;
+  auto it = h->gindex.find({std::min(id1, id2), std::max(id1, id2)});
+  return it == h->gindex.end() ? -1 : it->second;
+}
+
+int rpgo_lc_remove_last(rpgo_handle* h, int32_t gi, uint64_t* key_from, uint64_t* key_to) {
+  if (!h || gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
+  Group* g = h->groups[gi];
+  if (g->n <= 0) return RPGO_ERR_NOT_FOUND;
+  if (key_from) *key_from = g->kfrom.back();
+  if (key_to) *key_to = g->kto.back();
+  g->kfrom.pop_back();
+  g->kto.pop_back();
+  g->h_idxf.pop_back();
+  g->h_idxb.pop_back();
+  g->h_pfx.pop_back();
+  g->n -= 1;
+  if (h->loop_check && g->bits.p) {
+    launch_clear_last(g->bits.as<uint32_t>(), g->stride32, (int)g->n, h->stream);
+    launch_degree(g->bits.as<uint32_t>(), g->stride32, (int)g->n, g->deg.as<int32_t>(), h->stream);
+    h->launches += 2;
+    H_CHECK_CUDA(h, cudaGetLastError());
+  }
+  return RPGO_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+int rpgo_find_inliers(rpgo_handle* h, int32_t gi, int32_t clique_mode, int64_t n_new, int64_t prev_size,
+                      int32_t* ids_out, int64_t* size_out, int32_t* true_clique_out) {
+  if (!h || !ids_out || !size_out) return RPGO_ERR_INVALID;
+  if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
+  Group* g = h->groups[gi];
+  const int n = (int)g->n;
+  if (n <= 0 || !h->loop_check) { h->err = "find_inliers: empty group or loop check disabled"; return RPGO_ERR_INVALID; }
+  cudaStream_t st = h->stream;
+  const int W = (n + 31) / 32;
+  const int64_t blocks = 296;
+  H_CHECK_CUDA(h, h->c_degmask.ensure((size_t)W * 4 + 64, 0, st));
+  H_CHECK_CUDA(h, h->c_picks.ensure((size_t)n * 4 + 64, 0, st));
+  H_CHECK_CUDA(h, h->c_elim.ensure((size_t)n * 4 + 64, 0, st));
+  H_CHECK_CUDA(h, h->c_result.ensure((size_t)n * 4 + 64, 0, st));
+  H_CHECK_CUDA(h, h->c_ctl.ensure(64, 0, st));
+  H_CHECK_CUDA(h, h->c_rwork.ensure((size_t)blocks * n * 4 + (size_t)W * 8 + 64, 0, st));
+  CliqueScratch s;
+  s.degmask = h->c_degmask.as<uint32_t>();
+  s.picks = h->c_picks.as<int32_t>();
+  s.elim = h->c_elim.as<int32_t>();
+  s.result = h->c_result.as<int32_t>();
+  s.ctl = h->c_ctl.as<long long>();
+  s.rwork = h->c_rwork.as<uint32_t>();
+  s.rwork_blocks = blocks;
+  int r;
+  if (clique_mode == RPGO_CLIQUE_HEU) {
+    r = clique_heuristic(g->bits.as<uint32_t>(), g->stride32, n, g->deg.as<int32_t>(), 0, -1, s, ids_out, true_clique_out,
+                         &h->launches, st);
+    if (r < -1) { h->err = "clique_heuristic failed: " + std::to_string(r); return RPGO_ERR_CUDA; }
+    *size_out = r;
+  } else if (clique_mode == RPGO_CLIQUE_HEU_INCREMENTAL) {
+    if (n_new < 0 || n_new > n || prev_size < 0) return RPGO_ERR_INVALID;
+    r = clique_heuristic(g->bits.as<uint32_t>(), g->stride32, n, g->deg.as<int32_t>(), (int)(n - n_new), (int)prev_size, s,
+                         ids_out, true_clique_out, &h->launches, st);
+    if (r < -1) { h->err = "clique_heuristic failed: " + std::to_string(r); return RPGO_ERR_CUDA; }
+    *size_out = (r > prev_size) ? r : 0; /* GraphUtils.cpp:40-43 */
+  } else if (clique_mode == RPGO_CLIQUE_EXACT) {
+    r = clique_exact(g->bits.as<uint32_t>(), g->stride32, n, g->deg.as<int32_t>(), s, ids_out, &h->launches, st);
+    if (r < 0) { h->err = "clique_exact failed: " + std::to_string(r); return RPGO_ERR_CUDA; }
+    *size_out = r;
+  } else {
+    return RPGO_ERR_INVALID;
+  }
+  return RPGO_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+int rpgo_adj_bits(rpgo_handle* h, int32_t gi, uint64_t* rows_out, int64_t stride_words) {
+  if (!h || !rows_out) return RPGO_ERR_INVALID;
+  if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
+  Group* g = h->groups[gi];
+  const int64_t n = g->n;
+  if (stride_words < (n + 63) / 64) return RPGO_ERR_INVALID;
+  memset(rows_out, 0, (size_t)n * stride_words * 8);
+  if (!g->bits.p || n == 0) return RPGO_OK;
+  const size_t width = (size_t)((n + 31) / 32) * 4;
+  H_CHECK_CUDA(h, cudaMemcpy2DAsync(rows_out, (size_t)stride_words * 8, g->bits.p, (size_t)g->stride32 * 4, width, (size_t)n,
+                                    cudaMemcpyDeviceToHost, h->stream));
+  H_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+  return RPGO_OK;
+}
+
+int rpgo_adj_bits_device(rpgo_handle* h, int32_t gi, void** bits_device, int64_t* stride_words, int64_t* n) {
+  if (!h) return RPGO_ERR_INVALID;
+  if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
+  Group* g = h->groups[gi];
+  if (bits_device) *bits_device = g->bits.p;
+  if (stride_words) *stride_words = g->stride32 / 2;
+  if (n) *n = g->n;
+  return RPGO_OK;
+}
+
+int rpgo_degrees(rpgo_handle* h, int32_t gi, int32_t* deg_out) {
+  if (!h || !deg_out) return RPGO_ERR_INVALID;
+  if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
+  Group* g = h->groups[gi];
+  if (g->n == 0) return RPGO_OK;
+  H_CHECK_CUDA(h, cudaMemcpyAsync(deg_out, g->deg.p, (size_t)g->n * 4, cudaMemcpyDeviceToHost, h->stream));
+  H_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+  return RPGO_OK;
+}
+
+int rpgo_near_threshold(rpgo_handle* h, int32_t gi, int32_t* pairs_out, int64_t cap, int64_t* n_out) {
+  if (!h || !n_out) return RPGO_ERR_INVALID;
+  if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
+  Group* g = h->groups[gi];
+  *n_out = 0;
+  if (!g->fl_count.p) return RPGO_OK;
+  unsigned long long c = 0;
+  H_CHECK_CUDA(h, cudaMemcpyAsync(&c, g->fl_count.p, 8, cudaMemcpyDeviceToHost, h->stream));
+  H_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+  *n_out = (int64_t)c;
+  const int64_t m = std::min<int64_t>(std::min<int64_t>((int64_t)c, cap), FLAG_CAP);
+  if (pairs_out && m > 0) {
+    H_CHECK_CUDA(h, cudaMemcpyAsync(pairs_out, g->fl_pairs.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
+    H_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return RPGO_OK;
+}
+
+int rpgo_pair_distances(rpgo_handle* h, int32_t gi, double* dist_out) {
+  if (!h || !dist_out) return RPGO_ERR_INVALID;
+  if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
+  Group* g = h->groups[gi];
+  const int64_t n = g->n;
+  if (n > 8192) { h->err = "pair_distances is a debug call: n <= 8192"; return RPGO_ERR_INVALID; }
+  DevBuf dd;
+  H_CHECK_CUDA(h, dd.ensure((size_t)n * n * 8, 0, h->stream));
+  /* count is reset so that the recompute does not double-count flagged pairs */
+  unsigned long long saved = 0;
+  if (g->fl_count.p) H_CHECK_CUDA(h, cudaMemcpyAsync(&saved, g->fl_count.p, 8, cudaMemcpyDeviceToHost, h->stream));
+  H_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+  /* force all rows: temporarily single-GPU sharding */
+  const int w = h->cfg.world, r = h->cfg.rank;
+  h->cfg.world = 1; h->cfg.rank = 0;
+  int rc = run_pairwise(h, g, 0, dd.as<double>());
+  h->cfg.world = w; h->cfg.rank = r;
+  if (rc != RPGO_OK) return rc;
+  if (g->fl_count.p) H_CHECK_CUDA(h, cudaMemcpyAsync(g->fl_count.p, &saved, 8, cudaMemcpyHostToDevice, h->stream));
+  H_CHECK_CUDA(h, cudaMemcpyAsync(dist_out, dd.p, (size_t)n * n * 8, cudaMemcpyDeviceToHost, h->stream));
+  H_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+  return RPGO_OK;
+}
+
+int rpgo_group_recompute(rpgo_handle* h, int32_t gi, int64_t j_begin) {
+  if (!h) return RPGO_ERR_INVALID;
+  if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
+  Group* g = h->groups[gi];
+  if (j_begin < 0 || j_begin > g->n) return RPGO_ERR_INVALID;
+  if (g->fl_count.p) H_CHECK_CUDA(h, cudaMemsetAsync(g->fl_count.p, 0, 8, h->stream));
+  int rc = run_pairwise(h, g, j_begin, nullptr);
+  if (rc != RPGO_OK) return rc;
+  if (h->cfg.world <= 1) rc = finalize_group(h, g, j_begin);
+  return rc;
+}
+
+int rpgo_group_finalize(rpgo_handle* h, int32_t gi) {
+  if (!h) return RPGO_ERR_INVALID;
+  if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
+  return finalize_group(h, h->groups[gi], 0);
+}
+
+int rpgo_group_chunking(rpgo_handle* h, int32_t gi, int64_t* chunk_rows, int64_t* padded_rows) {
+  if (!h) return RPGO_ERR_INVALID;
+  if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
+  Shard s = group_shard(h, h->groups[gi]);
+  if (chunk_rows) *chunk_rows = s.chunk_rows;
+  if (padded_rows) *padded_rows = s.chunk_rows * 2 * s.world;
+  return RPGO_OK;
+}
+
+int rpgo_debug_load_group(rpgo_handle* h, uint8_t id1, uint8_t id2, int64_t n, const uint64_t* rows,
+                          int64_t stride_words, int32_t* group_out) {
+  if (!h || n < 0 || (n > 0 && !rows) || stride_words < (n + 63) / 64) return RPGO_ERR_INVALID;
+  if (!h->loop_check) return RPGO_ERR_INVALID;
+  const std::pair<uint8_t, uint8_t> id(std::min(id1, id2), std::max(id1, id2));
+  int32_t gi;
+  auto it = h->gindex.find(id);
+  if (it == h->gindex.end()) {
+    Group* g = new Group();
+    g->id1 = id.first;
+    g->id2 = id.second;
+    gi = (int32_t)h->groups.size();
+    h->groups.push_back(g);
+    h->gindex[id] = gi;
+  } else {
+    gi = it->second;
+  }
+  Group* g = h->groups[gi];
+  g->n = 0;
+  int rc = ensure_group(h, g, std::max<int64_t>(n, 1));
+  if (rc != RPGO_OK) return rc;
+  H_CHECK_CUDA(h, cudaMemsetAsync(g->bits.p, 0, g->bits.cap, h->stream));
+  if (n > 0)
+    H_CHECK_CUDA(h, cudaMemcpy2DAsync(g->bits.p, (size_t)g->stride32 * 4, rows, (size_t)stride_words * 8,
+                                      (size_t)((n + 31) / 32) * 4, (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  g->n = n;
+  g->kfrom.assign((size_t)n, 0);
+  g->kto.assign((size_t)n, 0);
+  g->h_idxf.assign((size_t)n, 0);
+  g->h_idxb.assign((size_t)n, 0);
+  g->h_pfx.assign((size_t)n, id.first);
+  launch_degree(g->bits.as<uint32_t>(), g->stride32, (int)n, g->deg.as<int32_t>(), h->stream);
+  h->launches++;
+  H_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (group_out) *group_out = gi;
+  return RPGO_OK;
+}
+
+int rpgo_fp64_peak(int32_t device, double* tflops_out) {
+  if (!tflops_out) return RPGO_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return RPGO_ERR_CUDA;
+  if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return RPGO_ERR_CUDA;
+  cudaStream_t st;
+  if (cudaStreamCreate(&st) != cudaSuccess) return RPGO_ERR_CUDA;
+  *tflops_out = fp64_peak_tflops(st);
+  cudaStreamDestroy(st);
+  return *tflops_out > 0 ? RPGO_OK : RPGO_ERR_CUDA;
+}
+
+}  /* extern "C" */

@@ -1,0 +1,331 @@
+/* clique_kernels.cu — inlier selection over the bitset adjacency (sm_100a).
+ *
+ *   K4  heuristic max clique   FMC::maxCliqueHeu / maxCliqueHeuIncremental
+ *                              (reference include/KimeraRPGO/max_clique_finder/findCliqueHeu.cpp:32-209,
+ *                               wrappers src/utils/GraphUtils.cpp:19-44), including the scratch-buffer
+ *                               contents the reference hands back (findCliqueHeu.cpp:110-113) which
+ *                               Pcm.h:865-869 consumes as "inlier indices".
+ *
+ * Reference algorithm per candidate v (ascending), with running bound maxClq:
+ *     skip if maxClq > deg(v);  S = [v] ++ [u in N(v) ascending : deg(u) >= maxClq]
+ *     repeat { pick = S.back(); S = [u in S : u in N(pick)]; icc++ } until S empty
+ *     if icc > maxClq { out = scratch buffer; maxClq = icc }
+ * Bitset formulation: R = N(v) & {deg >= maxClq}; pick = highest set bit of R; R &= N(pick);
+ * icc = 1 + number of picks.  Two exact accelerations:
+ *   - bound: steps + |R| + 1 <= maxClq  =>  icc cannot exceed maxClq  =>  the candidate cannot change
+ *     the reference's state, stop early;
+ *   - window resolution: all picks that fall into the current top 32-bit word of R are resolved by one
+ *     warp from a single 32x32 sub-block of the adjacency, then the remaining words are ANDed with all
+ *     of those picks' rows in one parallel sweep (one dependent memory round per window, not per pick).
+ * The sequential dependence between candidates (maxClq) is honoured by rounds: every candidate is
+ * evaluated against a snapshot of maxClq; the first candidate that improves it commits, later
+ * candidates are re-evaluated against the new bound (identical to the sequential order of events).
+ */
+#include <climits>
+#include <cstdio>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace rpgo {
+
+static constexpr int HEU_THREADS = 256;
+
+__global__ void degmask_kernel(const int32_t* __restrict__ deg, int n, int M, uint32_t* mask, int words) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= words) return;
+  uint32_t m = 0;
+#pragma unroll 4
+  for (int b = 0; b < 32; ++b) {
+    const int u = w * 32 + b;
+    if (u < n && deg[u] >= M) m |= 1u << b;
+  }
+  mask[w] = m;
+}
+
+/* block-wide (sum, max) reduction; returns to all threads */
+__device__ __forceinline__ void block_sum_max(int& s, int& m, int* sh) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  s = __reduce_add_sync(0xffffffffu, s);
+  m = __reduce_max_sync(0xffffffffu, m);
+  __syncthreads(); /* protect sh from the previous use */
+  if (lane == 0) {
+    sh[wid] = s;
+    sh[32 + wid] = m;
+  }
+  __syncthreads();
+  int ts = 0, tm = -1;
+  for (int i = 0; i < nw; ++i) {
+    ts += sh[i];
+    tm = max(tm, sh[32 + i]);
+  }
+  s = ts;
+  m = tm;
+}
+
+/* ctl[0]: packed (candidate << 32 | icc) of the lowest-index improving candidate of this round
+ *         (ULLONG_MAX = none).  picks_block: per-block pick log (n ints each). */
+__global__ void __launch_bounds__(HEU_THREADS) heu_round_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n,
+                                                                const int32_t* __restrict__ deg,
+                                                                const uint32_t* __restrict__ degmask, int first, int M,
+                                                                unsigned long long* ctl, int32_t* picks_block) {
+  extern __shared__ uint32_t R[];
+  __shared__ int sh[64];
+  __shared__ uint32_t s_P;
+  __shared__ int s_abort;
+  const int W = (n + 31) / 32;
+  const int tid = threadIdx.x;
+  int32_t* my_picks = picks_block + (size_t)blockIdx.x * n;
+
+  for (int v = first + blockIdx.x; v < n; v += gridDim.x) {
+    /* a lower-index candidate already improved: everything from here on is re-evaluated next round */
+    __syncthreads();
+    if (tid == 0) s_abort = ((long long)(*(volatile unsigned long long*)ctl >> 32) < (long long)v) ? 1 : 0;
+    __syncthreads();
+    if (s_abort) return;
+    if (M > deg[v]) continue; /* pruning 1 */
+    int cnt = 0, top = -1;
+    for (int w = tid; w < W; w += blockDim.x) {
+      const uint32_t r = bits[(size_t)v * stride32 + w] & degmask[w];
+      R[w] = r;
+      cnt += __popc(r);
+      if (r) top = w;
+    }
+    block_sum_max(cnt, top, sh);
+    if (cnt + 1 <= M) continue; /* cannot exceed the bound */
+    int steps = 0;
+    bool dead = false;
+    int iter = 0;
+    while (cnt > 0) {
+      if (steps + cnt + 1 <= M) { dead = true; break; }
+      if (tid == 0) s_abort = ((++iter & 7) == 0 && (long long)(*(volatile unsigned long long*)ctl >> 32) < (long long)v) ? 1 : 0;
+      const int t = top;
+      if (tid < 32) {
+        const uint32_t T = R[t];
+        const int lane = tid;
+        uint32_t rw = 0;
+        if ((T >> lane) & 1u) rw = bits[(size_t)(t * 32 + lane) * stride32 + t];
+        uint32_t cur = T, P = 0;
+        int k = 0;
+        while (cur) {
+          const int b = 31 - __clz(cur);
+          P |= 1u << b;
+          const uint32_t rb = __shfl_sync(0xffffffffu, rw, b);
+          cur &= rb & ~(1u << b);
+          if (lane == 0) my_picks[steps + k] = t * 32 + b;
+          ++k;
+        }
+        if (lane == 0) {
+          s_P = P;
+          R[t] = 0;
+        }
+      }
+      __syncthreads();
+      if (s_abort) return;
+      const uint32_t P = s_P;
+      steps += __popc(P);
+      cnt = 0;
+      top = -1;
+      for (int w = tid; w < t; w += blockDim.x) {
+        uint32_t r = R[w];
+        if (r) {
+          uint32_t q = P;
+          while (q && r) {
+            const int b = 31 - __clz(q);
+            q &= ~(1u << b);
+            r &= bits[(size_t)(t * 32 + b) * stride32 + w];
+          }
+          R[w] = r;
+          cnt += __popc(r);
+          if (r) top = w;
+        }
+      }
+      block_sum_max(cnt, top, sh);
+    }
+    if (dead) continue;
+    const int icc = steps + 1;
+    if (icc > M) {
+      if (tid == 0) atomicMin(ctl, ((unsigned long long)(unsigned)v << 32) | (unsigned)icc);
+      return; /* later candidates of this block are > v: re-evaluated next round */
+    }
+  }
+}
+
+/* elimination step of every vertex of the winner's initial list:
+ * e(u) = k such that u leaves the list when pick p_k is applied (p_1 > p_2 > ... > p_K), 0 if u was
+ * never in the list.  u leaves at the first (= highest-id) pick it is not adjacent to.
+ * pset: bitset of picks; above[w]: number of picks in words > w. */
+__global__ void heu_elim_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n, int v,
+                                const uint32_t* __restrict__ degmask, const uint32_t* __restrict__ pset,
+                                const int32_t* __restrict__ above, int32_t* elim) {
+  const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (u >= n) return;
+  const int W = (n + 31) / 32;
+  const bool in_r0 = ((bits[(size_t)v * stride32 + (u >> 5)] & degmask[u >> 5]) >> (u & 31)) & 1u;
+  if (!in_r0) {
+    if (lane == 0) elim[u] = 0;
+    return;
+  }
+  int e = 0;
+  for (int base = ((W - 1) / 32) * 32; base >= 0; base -= 32) {
+    const int w = base + lane;
+    uint32_t z = 0;
+    if (w < W) z = pset[w] & ~bits[(size_t)u * stride32 + w];
+    const unsigned nz = __ballot_sync(0xffffffffu, z != 0);
+    if (nz) {
+      const int hl = 31 - __clz(nz);
+      const uint32_t zz = __shfl_sync(0xffffffffu, z, hl);
+      const int ww = base + hl;
+      const int b = 31 - __clz(zz);
+      const uint32_t pw = pset[ww];
+      const int higher = (b == 31) ? 0 : __popc(pw >> (b + 1));
+      e = above[ww] + higher + 1;
+      break;
+    }
+  }
+  if (lane == 0) elim[u] = e;
+}
+
+/* out[p], p = 1..K: the (p-1)-th smallest u with elim[u] > kstar[p] (see DESIGN.md "scratch-buffer replay") */
+__global__ void heu_select_kernel(int n, int K, const int32_t* __restrict__ elim, const int32_t* __restrict__ kstar,
+                                  int32_t* out) {
+  const int p = 1 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (p > K) return;
+  const int ks = kstar[p];
+  int need = p - 1; /* rank to find */
+  int found = -1;
+  for (int base = 0; base < n; base += 32) {
+    const int u = base + lane;
+    const bool in = (u < n) && (elim[u] > ks);
+    const unsigned m = __ballot_sync(0xffffffffu, in);
+    const int c = __popc(m);
+    if (need < c) {
+      /* the need-th set bit of m */
+      unsigned mm = m;
+      for (int i = 0; i < need; ++i) mm &= mm - 1;
+      found = base + (__ffs(mm) - 1);
+      break;
+    }
+    need -= c;
+  }
+  if (lane == 0) out[p] = found;
+}
+
+#define CUCHECK(x)                                   \
+  do {                                               \
+    cudaError_t e_ = (x);                            \
+    if (e_ != cudaSuccess) return -(int)e_ - 1000;   \
+  } while (0)
+
+/* Host driver.  Returns the reference's return value (maxClq); ids_out_host gets the first maxClq
+ * entries of the reference's returned buffer; true_out_host (optional) the greedy clique itself. */
+int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_t* deg, int first, int maxclq0,
+                     CliqueScratch s, int32_t* ids_out_host, int32_t* true_out_host, int64_t* launches,
+                     cudaStream_t st) {
+  if (n <= 0) return -1;
+  const int W = (n + 31) / 32;
+  const size_t smem = (size_t)W * sizeof(uint32_t);
+  if (smem > 200 * 1024) return -2; /* n > ~1.6M closures in one group: not supported by this kernel */
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(heu_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  int M = maxclq0;
+  int winner = -1, winner_M = 0, winner_icc = 0, winner_block = 0;
+  int start = first < 0 ? 0 : first;
+  std::vector<int32_t> picks_host;
+  const int grid_cap = (int)s.rwork_blocks;
+  unsigned long long h_ctl;
+  while (start < n) {
+    const unsigned long long none = ~0ULL;
+    CUCHECK(cudaMemcpyAsync(s.ctl, &none, sizeof(none), cudaMemcpyHostToDevice, st));
+    degmask_kernel<<<(W + 127) / 128, 128, 0, st>>>(deg, n, M, s.degmask, W);
+    int grid = n - start;
+    if (grid > grid_cap) grid = grid_cap;
+    heu_round_kernel<<<grid, HEU_THREADS, smem, st>>>(bits, stride32, n, deg, s.degmask, start, M,
+                                                      (unsigned long long*)s.ctl, (int32_t*)s.rwork);
+    *launches += 2;
+    CUCHECK(cudaMemcpyAsync(&h_ctl, s.ctl, sizeof(h_ctl), cudaMemcpyDeviceToHost, st));
+    CUCHECK(cudaStreamSynchronize(st));
+    if (h_ctl == none) break;
+    winner = (int)(h_ctl >> 32);
+    winner_icc = (int)(h_ctl & 0xffffffffu);
+    winner_M = M;
+    winner_block = (winner - start) % grid;
+    /* keep the winner's pick log (its block may be reused next round) */
+    CUCHECK(cudaMemcpyAsync(s.picks, (int32_t*)s.rwork + (size_t)winner_block * n,
+                            sizeof(int32_t) * (size_t)(winner_icc - 1 > 0 ? winner_icc - 1 : 0), cudaMemcpyDeviceToDevice, st));
+    M = winner_icc;
+    start = winner + 1;
+  }
+  if (winner < 0) return M; /* no candidate improved on maxclq0 (incremental mode) */
+
+  const int K = winner_icc - 1;
+  picks_host.resize(K > 0 ? K : 1);
+  if (K > 0) CUCHECK(cudaMemcpyAsync(picks_host.data(), s.picks, sizeof(int32_t) * K, cudaMemcpyDeviceToHost, st));
+  CUCHECK(cudaStreamSynchronize(st));
+  if (true_out_host) {
+    true_out_host[0] = winner;
+    for (int k = 0; k < K; ++k) true_out_host[1 + k] = picks_host[k];
+  }
+  ids_out_host[0] = winner;
+  if (K == 0) return M;
+
+  /* ---- scratch-buffer replay ---- */
+  std::vector<uint32_t> pset(W, 0u);
+  for (int k = 0; k < K; ++k) pset[picks_host[k] >> 5] |= 1u << (picks_host[k] & 31);
+  std::vector<int32_t> above(W, 0);
+  for (int w = W - 2; w >= 0; --w) above[w] = above[w + 1] + __builtin_popcount(pset[w + 1]);
+  /* device temporaries reuse s.rwork (the pick logs are no longer needed) */
+  uint32_t* d_pset = s.rwork;
+  int32_t* d_above = (int32_t*)(s.rwork + W);
+  int32_t* d_kstar = d_above + W;
+  CUCHECK(cudaMemcpyAsync(d_pset, pset.data(), sizeof(uint32_t) * W, cudaMemcpyHostToDevice, st));
+  CUCHECK(cudaMemcpyAsync(d_above, above.data(), sizeof(int32_t) * W, cudaMemcpyHostToDevice, st));
+  degmask_kernel<<<(W + 127) / 128, 128, 0, st>>>(deg, n, winner_M, s.degmask, W);
+  heu_elim_kernel<<<(n + 7) / 8, 256, 0, st>>>(bits, stride32, n, winner, s.degmask, d_pset, d_above, s.elim);
+  *launches += 2;
+  std::vector<int32_t> elim(n);
+  CUCHECK(cudaMemcpyAsync(elim.data(), s.elim, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  CUCHECK(cudaStreamSynchronize(st));
+  /* cnt[k] = #{u : elim[u] > k}, k = 0..K  (list k has 1 + cnt[k] entries) */
+  std::vector<int64_t> hist(K + 2, 0);
+  for (int u = 0; u < n; ++u)
+    if (elim[u] > 0) hist[elim[u] <= K ? elim[u] : K + 1]++;
+  std::vector<int64_t> cnt(K + 1, 0);
+  {
+    int64_t acc = hist[K + 1];
+    for (int k = K; k >= 0; --k) {
+      cnt[k] = acc; /* elim > k */
+      acc += hist[k];
+    }
+  }
+  /* kstar[p] = max{k <= K : cnt[k] >= p}; cnt is non-increasing, cnt[K - p] >= p always */
+  std::vector<int32_t> kstar(K + 1, 0);
+  {
+    int k = K;
+    for (int p = 1; p <= K; ++p) {
+      while (k > 0 && cnt[k] < p) --k;
+      kstar[p] = k;
+    }
+  }
+  CUCHECK(cudaMemcpyAsync(d_kstar, kstar.data(), sizeof(int32_t) * (K + 1), cudaMemcpyHostToDevice, st));
+  heu_select_kernel<<<(K + 7) / 8, 256, 0, st>>>(n, K, s.elim, d_kstar, s.result);
+  *launches += 1;
+  CUCHECK(cudaMemcpyAsync(ids_out_host + 1, s.result + 1, sizeof(int32_t) * K, cudaMemcpyDeviceToHost, st));
+  CUCHECK(cudaStreamSynchronize(st));
+  return M;
+}
+
+}  // namespace rpgo
+
+namespace rpgo {
+/* K5 placeholder until the exact branch-and-bound lands (see clique_exact.cu) */
+__attribute__((weak)) int clique_exact(const uint32_t*, int64_t, int, const int32_t*, CliqueScratch, int32_t*, int64_t*,
+                                       cudaStream_t) {
+  return -3;
+}
+}  // namespace rpgo

@@ -1,0 +1,85 @@
+/* kernels.cuh — internal launcher declarations shared by the .cu files and the C-ABI layer. */
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rpgo_math.cuh"
+
+namespace rpgo {
+
+/* one odometry step: entries[out_idx] = entries[prev_idx] (or the running value) . T(delta) */
+struct FoldChain {
+  int32_t first_step;  /* index of the chain's first step in the step arrays */
+  int32_t n_steps;
+  int32_t start_idx;   /* trajectory entry the chain starts from */
+  int32_t pad;
+};
+
+/* device view of one ObservationId group */
+struct GroupView {
+  const double* lc;          /* n x ENTRY closure entries (AoS), after the from-factor constructor */
+  const int32_t* idx_front;  /* trajectory entry index of key_from (0 = default/identity entry) */
+  const int32_t* idx_back;   /* trajectory entry index of key_to */
+  const uint8_t* pfx_front;  /* Symbol::chr() of key_from (decides the Pcm.h:691-698 key swap) */
+  uint32_t* bits;            /* adjacency bitset, row stride stride32 32-bit words */
+  int64_t stride32;
+  int32_t* deg;
+  int32_t n;
+};
+
+struct Flagged {
+  int32_t* pairs;                 /* 2 ints per flagged pair */
+  unsigned long long* count;      /* total flagged (may exceed cap) */
+  int64_t cap;
+};
+
+/* row sharding for multi-GPU: rows are cut into 2*world chunks of chunk_rows; this rank owns chunks
+ * rank and 2*world-1-rank.  world == 1 => everything. */
+struct Shard {
+  int32_t rank, world;
+  int64_t chunk_rows;
+};
+
+/* K1 */
+void launch_traj_fold(int dim, int mode, int n_chains, const FoldChain* chains, const int32_t* out_idx,
+                      const double* delta_pose, const double* delta_cov, double* entries, cudaStream_t st);
+void launch_traj_scan_phases(int dim, int mode, int n_chains, const FoldChain* chains, const int32_t* out_idx,
+                             const double* delta_pose, const double* delta_cov, double* entries, int chunk,
+                             int total_steps, int total_chunks, const int32_t* chunk_chain, const int32_t* chunk_first,
+                             const int32_t* chain_first_chunk, const int32_t* step_chunk, double* carry,
+                             cudaStream_t st);
+/* raw (pose, cov) -> entries; K2 odometry check for the ones with check[i] != 0 */
+void launch_lc_prepare(int dim, int mode, int n, const double* pose, const double* cov, const int32_t* idx_front,
+                       const int32_t* idx_back, const uint8_t* check, const double* traj, Thresholds th,
+                       double* entries_out, uint8_t* ok_out, double* dist_out, cudaStream_t st);
+void launch_scatter_entries(int dim, int n, const double* entries, const uint64_t* dst_ptrs, cudaStream_t st);
+/* K3 */
+void launch_pairwise_direct(int dim, int mode, GroupView g, const double* traj, int j_begin, Shard sh, Thresholds th,
+                            Flagged fl, double* dist_out, cudaStream_t st);
+void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* traj, int j_begin, Shard sh, Thresholds th,
+                           Flagged fl, cudaStream_t st);
+/* bitset maintenance */
+void launch_mirror(uint32_t* bits, int64_t stride32, int n, int j_begin, cudaStream_t st);
+void launch_degree(const uint32_t* bits, int64_t stride32, int n, int32_t* deg, cudaStream_t st);
+void launch_clear_last(uint32_t* bits, int64_t stride32, int n_after, cudaStream_t st);
+
+/* K4: heuristic clique.  Returns through host pointers (synchronises the stream). */
+struct CliqueScratch {
+  uint32_t* degmask;        /* stride32 words */
+  int32_t* picks;           /* n */
+  int32_t* elim;            /* n */
+  int32_t* result;          /* n */
+  long long* ctl;           /* control words: [0] first improver, [1] its icc, ... */
+  uint32_t* rwork;          /* per-block working sets: grid x stride32 */
+  int64_t rwork_blocks;
+};
+int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_t* deg, int first, int maxclq0,
+                     CliqueScratch s, int32_t* ids_out_host, int32_t* true_out_host, int64_t* launches,
+                     cudaStream_t st);
+int clique_exact(const uint32_t* bits, int64_t stride32, int n, const int32_t* deg, CliqueScratch s,
+                 int32_t* ids_out_host, int64_t* launches, cudaStream_t st);
+
+double fp64_peak_tflops(cudaStream_t st);
+
+}  // namespace rpgo

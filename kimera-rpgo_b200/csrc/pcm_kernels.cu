@@ -1,0 +1,384 @@
+/* pcm_kernels.cu — sm_100a kernels for the PCM consistency stage.
+ *
+ *   K1  traj_fold / traj_scan   cumulative pose + covariance along each robot's odometry chain
+ *                               (replaces Pcm::updateOdom's left fold, reference Pcm.h:545-556)
+ *   K2  lc_prepare              PoseWithCovariance/PoseWithNode ctor from the factor + odometry
+ *                               consistency check (Pcm.h:604-629, GeometryUtils.h:91-115)
+ *   K3  pairwise_direct         one thread per (older i, newer j) closure pair: areLoopsConsistent
+ *                               (Pcm.h:670-718) -> warp-ballot packed adjacency words
+ *       mirror / degree / clear_last   bitset maintenance (symmetric fill, popcount degrees,
+ *                               removeLastLoopClosure's shrink Pcm.h:320-323)
+ * The tiled TMA variant of K3 lives in pcm_tiled.cu.
+ * Compile: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (the numerical contract forbids
+ * implicit contraction; all fused operations are explicit fma() calls in rpgo_math.cuh).
+ */
+#include <cstdio>
+
+#include "kernels.cuh"
+
+namespace rpgo {
+
+#define RPGO_DISPATCH(dim, mode, CALL)                         \
+  do {                                                         \
+    if ((dim) == 3 && (mode) == MODE_PCM) { CALL(3, MODE_PCM); }       \
+    else if ((dim) == 3) { CALL(3, MODE_SIMPLE); }             \
+    else if ((mode) == MODE_PCM) { CALL(2, MODE_PCM); }        \
+    else { CALL(2, MODE_SIMPLE); }                             \
+  } while (0)
+
+/* ------------------------------------------------------------------------------------------------
+ * K1: exact left fold, one thread per chain.  Sequential by definition (the reference's rounding is
+ * that of a strict left fold); chains (robots) run in parallel.
+ * ---------------------------------------------------------------------------------------------- */
+template <int D, int MODE>
+__global__ void traj_fold_kernel(int n_chains, const FoldChain* __restrict__ chains, const int32_t* __restrict__ out_idx,
+                                 const double* __restrict__ dpose, const double* __restrict__ dcov, double* entries) {
+  constexpr int E = Dim<D>::ENTRY, PS = Dim<D>::PS, NN = Dim<D>::N * Dim<D>::N;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chains) return;
+  const FoldChain ch = chains[c];
+  PoseT<D, MODE> cur, delta, nxt;
+  load_entry<D, MODE>(entries + (size_t)ch.start_idx * E, 1, cur);
+  for (int s = 0; s < ch.n_steps; ++s) {
+    const int k = ch.first_step + s;
+    from_factor<D, MODE>(dpose + (size_t)k * PS, dcov + (size_t)k * NN, delta);
+    pt_compose<D, MODE>(cur, delta, nxt);
+    store_entry<D, MODE>(entries + (size_t)out_idx[k] * E, 1, nxt);
+    cur = nxt;
+  }
+}
+
+void launch_traj_fold(int dim, int mode, int n_chains, const FoldChain* chains, const int32_t* out_idx,
+                      const double* delta_pose, const double* delta_cov, double* entries, cudaStream_t st) {
+  if (n_chains <= 0) return;
+  /* one chain per block so that independent robots land on different SMs */
+  const int blocks = n_chains;
+#define CALL(D, M) traj_fold_kernel<D, M><<<blocks, 1, 0, st>>>(n_chains, chains, out_idx, delta_pose, delta_cov, entries)
+  RPGO_DISPATCH(dim, mode, CALL);
+#undef CALL
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K1 (scan): three-phase chunked prefix scan over the associative operator
+ *   (Ta,Sa) o (Tb,Sb) = (Ta Tb, Ad(Tb^-1) Sa Ad(Tb^-1)^T + Sb).
+ * phase 1: each chunk folds its steps from the identity (parallel over chunks)
+ * phase 2: chunk totals are folded sequentially per chain (n_steps/chunk long)
+ * phase 3: every element is prefixed by its chunk's carry (parallel over elements)
+ * Deterministic, but re-associated w.r.t. the reference's strict left fold.
+ * scratch: per chunk one ENTRY (carry-in), laid out after the per-step local prefixes in `entries`'
+ * output slots (local prefixes are written to the final slots first, then overwritten in phase 3).
+ * ---------------------------------------------------------------------------------------------- */
+template <int D, int MODE>
+__global__ void traj_scan_phase1(int total_chunks, int chunk, const FoldChain* __restrict__ chains, int n_chains,
+                                 const int32_t* __restrict__ chunk_chain, const int32_t* __restrict__ chunk_first,
+                                 const int32_t* __restrict__ out_idx, const double* __restrict__ dpose,
+                                 const double* __restrict__ dcov, double* entries) {
+  constexpr int E = Dim<D>::ENTRY, PS = Dim<D>::PS, NN = Dim<D>::N * Dim<D>::N;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= total_chunks) return;
+  const FoldChain ch = chains[chunk_chain[q]];
+  const int s0 = chunk_first[q];
+  const int s1 = min(s0 + chunk, ch.first_step + ch.n_steps);
+  PoseT<D, MODE> cur, delta, nxt;
+  pose_identity<D>(cur.pose);
+  if (MODE == MODE_PCM) {
+#pragma unroll
+    for (int i = 0; i < NN; ++i) cur.cov[i] = 0.0;
+  }
+  cur.node = 0;
+  cur.rot = true;
+  for (int k = s0; k < s1; ++k) {
+    from_factor<D, MODE>(dpose + (size_t)k * PS, dcov + (size_t)k * NN, delta);
+    pt_compose<D, MODE>(cur, delta, nxt);
+    store_entry<D, MODE>(entries + (size_t)out_idx[k] * E, 1, nxt);
+    cur = nxt;
+  }
+}
+
+template <int D, int MODE>
+__global__ void traj_scan_phase2(int n_chains, int chunk, const FoldChain* __restrict__ chains,
+                                 const int32_t* __restrict__ chain_first_chunk, const int32_t* __restrict__ out_idx,
+                                 const double* entries, double* carry) {
+  constexpr int E = Dim<D>::ENTRY;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chains) return;
+  const FoldChain ch = chains[c];
+  const int nchunks = (ch.n_steps + chunk - 1) / chunk;
+  PoseT<D, MODE> cur, tot, nxt;
+  load_entry<D, MODE>(entries + (size_t)ch.start_idx * E, 1, cur);
+  for (int q = 0; q < nchunks; ++q) {
+    store_entry<D, MODE>(carry + (size_t)(chain_first_chunk[c] + q) * E, 1, cur);
+    const int last = min(ch.first_step + (q + 1) * chunk, ch.first_step + ch.n_steps) - 1;
+    load_entry<D, MODE>(entries + (size_t)out_idx[last] * E, 1, tot);
+    pt_compose<D, MODE>(cur, tot, nxt);
+    cur = nxt;
+  }
+}
+
+template <int D, int MODE>
+__global__ void traj_scan_phase3(int total_steps, int chunk, const int32_t* __restrict__ step_chunk,
+                                 const int32_t* __restrict__ out_idx, const double* carry, double* entries) {
+  constexpr int E = Dim<D>::ENTRY;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= total_steps) return;
+  PoseT<D, MODE> g, l, o;
+  load_entry<D, MODE>(carry + (size_t)step_chunk[k] * E, 1, g);
+  load_entry<D, MODE>(entries + (size_t)out_idx[k] * E, 1, l);
+  pt_compose<D, MODE>(g, l, o);
+  store_entry<D, MODE>(entries + (size_t)out_idx[k] * E, 1, o);
+}
+
+void launch_traj_scan_phases(int dim, int mode, int n_chains, const FoldChain* chains, const int32_t* out_idx,
+                             const double* delta_pose, const double* delta_cov, double* entries, int chunk,
+                             int total_steps, int total_chunks, const int32_t* chunk_chain, const int32_t* chunk_first,
+                             const int32_t* chain_first_chunk, const int32_t* step_chunk, double* carry,
+                             cudaStream_t st) {
+  if (total_steps <= 0) return;
+  const int T = 64;
+#define CALL(D, M)                                                                                                  \
+  traj_scan_phase1<D, M><<<(total_chunks + T - 1) / T, T, 0, st>>>(total_chunks, chunk, chains, n_chains, chunk_chain, \
+                                                                  chunk_first, out_idx, delta_pose, delta_cov, entries); \
+  traj_scan_phase2<D, M><<<n_chains, 1, 0, st>>>(n_chains, chunk, chains, chain_first_chunk, out_idx, entries, carry); \
+  traj_scan_phase3<D, M><<<(total_steps + T - 1) / T, T, 0, st>>>(total_steps, chunk, step_chunk, out_idx, carry, entries)
+  RPGO_DISPATCH(dim, mode, CALL);
+#undef CALL
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K2: closure constructor + odometry consistency check, one thread per new closure.
+ *   result = getBetween(i, j).compose(T(lc).inverse());  ok = dist < threshold   (Pcm.h:604-629)
+ * ---------------------------------------------------------------------------------------------- */
+template <int D, int MODE>
+__global__ void lc_prepare_kernel(int n, const double* __restrict__ pose, const double* __restrict__ cov,
+                                  const int32_t* __restrict__ idx_front, const int32_t* __restrict__ idx_back,
+                                  const uint8_t* __restrict__ check, const double* __restrict__ traj, Thresholds th,
+                                  double* entries_out, uint8_t* ok_out, double* dist_out) {
+  constexpr int E = Dim<D>::ENTRY, PS = Dim<D>::PS, NN = Dim<D>::N * Dim<D>::N;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  PoseT<D, MODE> lc;
+  from_factor<D, MODE>(pose + (size_t)k * PS, cov + (size_t)k * NN, lc);
+  store_entry<D, MODE>(entries_out + (size_t)k * E, 1, lc);
+  bool ok = true;
+  double dist = nan("");
+  if (check[k]) {
+    PoseT<D, MODE> a, b, pij, res;
+    load_entry<D, MODE>(traj + (size_t)idx_front[k] * E, 1, a);
+    load_entry<D, MODE>(traj + (size_t)idx_back[k] * E, 1, b);
+    pt_between<D, MODE>(a, b, pij);
+    pt_inverse_inplace<D, MODE>(lc);
+    pt_compose<D, MODE>(pij, lc, res);
+    bool near;
+    ok = check_consistent<D, MODE>(res, th, true, &dist, &near);
+  }
+  ok_out[k] = ok ? 1 : 0;
+  dist_out[k] = dist;
+}
+
+void launch_lc_prepare(int dim, int mode, int n, const double* pose, const double* cov, const int32_t* idx_front,
+                       const int32_t* idx_back, const uint8_t* check, const double* traj, Thresholds th,
+                       double* entries_out, uint8_t* ok_out, double* dist_out, cudaStream_t st) {
+  if (n <= 0) return;
+  const int T = 64;
+#define CALL(D, M) \
+  lc_prepare_kernel<D, M><<<(n + T - 1) / T, T, 0, st>>>(n, pose, cov, idx_front, idx_back, check, traj, th, entries_out, ok_out, dist_out)
+  RPGO_DISPATCH(dim, mode, CALL);
+#undef CALL
+}
+
+__global__ void scatter_entries_kernel(int n, int E, const double* __restrict__ entries, const uint64_t* __restrict__ dst) {
+  const int k = blockIdx.x;
+  if (k >= n) return;
+  const uint64_t d = dst[k];
+  if (d == 0) return;
+  double* out = reinterpret_cast<double*>(d);
+  for (int i = threadIdx.x; i < E; i += blockDim.x) out[i] = entries[(size_t)k * E + i];
+}
+void launch_scatter_entries(int dim, int n, const double* entries, const uint64_t* dst_ptrs, cudaStream_t st) {
+  if (n <= 0) return;
+  const int E = dim == 3 ? Dim<3>::ENTRY : Dim<2>::ENTRY;
+  scatter_entries_kernel<<<n, 64, 0, st>>>(n, E, entries, dst_ptrs);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K3 (direct): warp = one older closure i x 32 consecutive newer closures j; lane = j.
+ * The 32 decisions are packed with one __ballot_sync into the adjacency word (i, j/32).
+ * Operands are gathered straight from the global tables (L2-resident); this is the reference
+ * kernel the tiled variant is validated against.
+ * ---------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ bool row_owned(const Shard& sh, int i) {
+  if (sh.world <= 1) return true;
+  const int64_t c = i / sh.chunk_rows;
+  return c == sh.rank || c == 2 * (int64_t)sh.world - 1 - sh.rank;
+}
+
+template <int D, int MODE>
+__global__ void __launch_bounds__(128) pairwise_direct_kernel(GroupView g, const double* __restrict__ traj, int j_begin, int w_begin,
+                                                              Shard sh, Thresholds th, Flagged fl, double* dist_out) {
+  constexpr int E = Dim<D>::ENTRY;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int w = w_begin + blockIdx.x;                 /* adjacency word (32 columns) */
+  const int i = blockIdx.y * (blockDim.x >> 5) + wib; /* older closure */
+  const int j = w * 32 + lane;                        /* newer closure */
+  if (i >= g.n || i >= w * 32 + 31) return;           /* whole word on/below the diagonal */
+  if (!row_owned(sh, i)) return;
+  bool ok = false;
+  if (j < g.n && j > i && j >= j_begin) {
+    const uint8_t pa = g.pfx_front[i], pc = g.pfx_front[j];
+    const int ia = g.idx_front[i], ib = g.idx_back[i];
+    int ic = g.idx_front[j], id = g.idx_back[j];
+    if (pa != pc) { const int t = ic; ic = id; id = t; } /* Pcm.h:691-698: keys swapped, measurement not inverted */
+    double dist;
+    bool near;
+    ok = pair_check<D, MODE>(traj + (size_t)ia * E, 1, traj + (size_t)ib * E, 1, g.lc + (size_t)i * E, 1,
+                             traj + (size_t)ic * E, 1, traj + (size_t)id * E, 1, g.lc + (size_t)j * E, 1, th, &dist,
+                             &near);
+    if (near) {
+      const unsigned long long slot = atomicAdd(fl.count, 1ULL);
+      if ((int64_t)slot < fl.cap) {
+        fl.pairs[2 * slot] = i;
+        fl.pairs[2 * slot + 1] = j;
+      }
+    }
+    if (dist_out) {
+      dist_out[(size_t)i * g.n + j] = dist;
+      dist_out[(size_t)j * g.n + i] = dist;
+    }
+  }
+  const unsigned word = __ballot_sync(0xffffffffu, ok);
+  if (lane == 0) {
+    /* keep bits of columns < j_begin (computed earlier); columns <= i belong to the mirror pass */
+    unsigned keep = 0;
+    if (j_begin > w * 32) keep = (j_begin >= w * 32 + 32) ? 0xffffffffu : ((1u << (j_begin - w * 32)) - 1u);
+    uint32_t* p = g.bits + (size_t)i * g.stride32 + w;
+    *p = (*p & keep) | word;
+  }
+}
+
+void launch_pairwise_direct(int dim, int mode, GroupView g, const double* traj, int j_begin, Shard sh, Thresholds th,
+                            Flagged fl, double* dist_out, cudaStream_t st) {
+  if (g.n < 2 || j_begin >= g.n) return;
+  const int w_begin = j_begin / 32;
+  const int w_end = (g.n + 31) / 32;
+  const int warps = 4;
+  dim3 grid(w_end - w_begin, (g.n + warps - 1) / warps);
+#define CALL(D, M) pairwise_direct_kernel<D, M><<<grid, warps * 32, 0, st>>>(g, traj, j_begin, w_begin, sh, th, fl, dist_out)
+  RPGO_DISPATCH(dim, mode, CALL);
+#undef CALL
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * mirror: fill row j (columns i < j) from column j of rows i < j, for rows j >= j_begin.
+ * One warp transposes a 32x32 bit block with 32 ballots.
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void mirror_kernel(uint32_t* bits, int64_t stride32, int n, int wj_begin) {
+  const int lane = threadIdx.x & 31;
+  const int wj = wj_begin + blockIdx.x;                         /* destination rows 32*wj .. +31 */
+  const int wi = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5); /* source rows 32*wi .. +31 */
+  if (wi > wj) return;
+  const int i = wi * 32 + lane;
+  /* source word: row i, columns 32*wj.. ; only the strictly-upper part (col > row) is authoritative */
+  uint32_t src = 0;
+  if (i < n) {
+    src = bits[(size_t)i * stride32 + wj];
+    if (wi == wj) src &= (lane == 31) ? 0u : (0xffffffffu << (lane + 1));
+  }
+  uint32_t mine = 0;
+#pragma unroll
+  for (int b = 0; b < 32; ++b) {
+    const unsigned col = __ballot_sync(0xffffffffu, (src >> b) & 1u); /* column 32*wj+b over rows 32*wi.. */
+    if (lane == b) mine = col;
+  }
+  const int j = wj * 32 + lane;
+  if (j < n) {
+    uint32_t* p = bits + (size_t)j * stride32 + wi;
+    if (wi == wj) {
+      /* diagonal block: keep this row's own upper part, set the lower part */
+      const uint32_t upper_mask = (lane == 31) ? 0u : (0xffffffffu << (lane + 1));
+      *p = (*p & upper_mask) | (mine & ~upper_mask & ~(1u << lane));
+    } else {
+      *p = mine;
+    }
+  }
+}
+
+void launch_mirror(uint32_t* bits, int64_t stride32, int n, int j_begin, cudaStream_t st) {
+  if (n < 2 || j_begin >= n) return;
+  const int wj_begin = j_begin / 32;
+  const int wj_end = (n + 31) / 32;
+  const int warps = 4;
+  dim3 grid(wj_end - wj_begin, (wj_end + warps - 1) / warps);
+  mirror_kernel<<<grid, warps * 32, 0, st>>>(bits, stride32, n, wj_begin);
+}
+
+/* degree: popcount of each row, one warp per row */
+__global__ void degree_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n, int32_t* deg) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const int words = (n + 31) / 32;
+  int c = 0;
+  for (int w = lane; w < words; w += 32) c += __popc(bits[(size_t)row * stride32 + w]);
+  c = __reduce_add_sync(0xffffffffu, c);
+  if (lane == 0) deg[row] = c;
+}
+void launch_degree(const uint32_t* bits, int64_t stride32, int n, int32_t* deg, cudaStream_t st) {
+  if (n <= 0) return;
+  const int warps = 8;
+  degree_kernel<<<(n + warps - 1) / warps, warps * 32, 0, st>>>(bits, stride32, n, deg);
+}
+
+/* removeLastLoopClosure: clear row n_after and column n_after (Pcm.h:320-323 keeps the leading block) */
+__global__ void clear_last_kernel(uint32_t* bits, int64_t stride32, int n_after) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int words = (n_after + 32) / 32;
+  if (t < n_after) bits[(size_t)t * stride32 + n_after / 32] &= ~(1u << (n_after & 31));
+  if (t < words) bits[(size_t)n_after * stride32 + t] = 0u;
+}
+void launch_clear_last(uint32_t* bits, int64_t stride32, int n_after, cudaStream_t st) {
+  const int T = 128;
+  clear_last_kernel<<<(n_after + 1 + T - 1) / T + 1, T, 0, st>>>(bits, stride32, n_after);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * FP64 peak micro-benchmark (roofline denominator for K3): 8 independent DFMA chains per thread.
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+double fp64_peak_tflops(cudaStream_t st) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int threads = 512, blocks = sms * 4, iters = 1 << 15;
+  double* out = nullptr;
+  if (cudaMalloc(&out, sizeof(double) * threads * blocks) != cudaSuccess) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, st);
+    dfma_peak_kernel<<<blocks, threads, 0, st>>>(out, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 8.0 * (double)iters * threads * blocks;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  return best;
+}
+
+}  // namespace rpgo

@@ -1,0 +1,384 @@
+"""Host-side mirror of the reference's OutlierRemoval plug-in for the PCM path, on top of the C ABI.
+
+`PcmGpu` keeps exactly what Pcm<poseT,T> keeps on the host — factor classification, the odometry /
+special / per-group factor lists, ignored prefixes, output-graph assembly (reference
+include/KimeraRPGO/outlier/Pcm.h:148-281, :299-408, :977-1005) — and sends the three arithmetic stages
+to the GPU through include/rpgo_b200.h (odometry cache, pairwise consistency, max clique).
+Factors are plain tuples (type, key1, key2, pose, cov) and values (key, pose), i.e. what a
+gtsam::BetweenFactor / PriorFactor / Values entry carries; the C++ adapter in INTEGRATION.md maps
+GTSAM objects onto the same calls.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+
+BETWEEN, PRIOR, OTHER = 0, 1, 2
+MODE_PCM, MODE_SIMPLE = 0, 1
+CLIQUE_HEU, CLIQUE_HEU_INCREMENTAL, CLIQUE_EXACT = 0, 1, 2
+TRAJ_FOLD, TRAJ_SCAN = 0, 1
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TILED = 0, 1, 2
+
+
+def key_chr(k):
+    return (int(k) >> 56) & 0xFF
+
+
+def _dp(a):
+    return a.ctypes.data_as(_capi.c_dp)
+
+
+class RpgoError(RuntimeError):
+    pass
+
+
+class PcmGpu:
+    """OutlierRemoval interface (OutlierRemoval.h:19-102) for Pcm2D/Pcm3D/PcmSimple2D/PcmSimple3D."""
+
+    def __init__(self, d=3, mode=MODE_PCM, odom_threshold=10.0, lc_threshold=5.0, odom_trans=0.05, odom_rot=0.005,
+                 dist_trans=0.01, dist_rot=0.001, incremental=False, device=-1, traj_mode=TRAJ_FOLD,
+                 kernel=KERNEL_AUTO, rank=0, world=1, special_symbols=(), scan_chunk=64):
+        self.lib = _capi.load()
+        cfg = _capi.RpgoCfg()
+        self.lib.rpgo_default_cfg(C.byref(cfg))
+        cfg.dim, cfg.mode = d, mode
+        cfg.odom_threshold, cfg.lc_threshold = odom_threshold, lc_threshold
+        cfg.odom_trans_threshold, cfg.odom_rot_threshold = odom_trans, odom_rot
+        cfg.dist_trans_threshold, cfg.dist_rot_threshold = dist_trans, dist_rot
+        cfg.incremental = int(incremental)
+        cfg.device, cfg.traj_mode, cfg.kernel, cfg.rank, cfg.world = device, traj_mode, kernel, rank, world
+        cfg.scan_chunk = scan_chunk
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        rc = self.lib.rpgo_create(C.byref(cfg), C.byref(self.h))
+        if rc != 0:
+            raise RpgoError("rpgo_create failed with status %d (no usable CUDA device? there is no CPU fallback)" % rc)
+        self.d, self.mode = d, mode
+        self.ps = 12 if d == 3 else 4
+        self.n = 6 if d == 3 else 3
+        self.incremental = bool(incremental)
+        # Pcm.h:74-82
+        self.odom_check = not (odom_threshold < 0 or odom_rot < 0 or odom_trans < 0)
+        self.loop_check = not (lc_threshold < 0 or dist_rot < 0 or dist_trans < 0)
+        self.special_symbols = set(ord(c) if isinstance(c, str) else int(c) for c in special_symbols)
+        self.values = {}
+        self.nfg_odom, self.nfg_special = [], []
+        self.special_is_prior = {}     # factor id -> prior key (for removePriorFactorsWithPrefix)
+        self.group_factors = {}        # group ordinal -> [factor ids]
+        self.group_consistent = {}     # group ordinal -> [factor ids]
+        self.group_order = []
+        self.lc_in_order = []
+        self.ignored = []
+        self.total_lc = 0
+        self.total_good_lc = 0
+        self.next_id = 0
+        self.output = []
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.rpgo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RpgoError("%s failed (%d): %s" % (what, rc, self.lib.rpgo_last_error(self.h).decode()))
+
+    # ---- OutlierRemoval::removeOutliers (Pcm.h:148-281) ---------------------------------------
+    def update(self, factors, values):
+        """One removeOutliers() call.  Returns do_optimize."""
+        new_keys = set()
+        for k, p in values:
+            self.values[int(k)] = np.asarray(p, dtype=np.float64)
+            new_keys.add(int(k))
+        if len(factors) == 0:
+            return False
+        do_optimize = False
+        odom, lcs = [], []
+        for f in factors:
+            fid = self.next_id
+            self.next_id += 1
+            ftype, k1, k2 = f[0], int(f[1]), int(f[2])
+            if ftype == BETWEEN:
+                if key_chr(k1) in self.special_symbols or key_chr(k2) in self.special_symbols:
+                    raise NotImplementedError("landmark (special symbol) factors are SURVEY §8(f) N3: not built yet")
+                if k1 + 1 == k2 and k2 in new_keys:
+                    odom.append((fid, k1, k2, f[3], f[4]))
+                elif k1 != k2:
+                    lcs.append((fid, k1, k2, f[3], f[4]))
+            else:
+                self.nfg_special.append(fid)
+                if ftype == PRIOR:
+                    self.special_is_prior[fid] = k1
+                do_optimize = True
+        # the reference folds each odometry factor as it meets it and processes all loop closures
+        # after the loop (Pcm.h:203-206 vs :242-246), so batching odometry first is order-preserving
+        if odom:
+            self._odom_append(odom)
+        if lcs:
+            num_new = self._lc_append(lcs)
+            if self.incremental:
+                self._find_inliers_incremental(num_new)
+            else:
+                self._find_inliers()
+            do_optimize = True
+        self._build_graph()
+        return do_optimize
+
+    def _odom_append(self, odom):
+        n = len(odom)
+        prev = np.array([o[1] for o in odom], dtype=np.uint64)
+        new = np.array([o[2] for o in odom], dtype=np.uint64)
+        dpose = np.ascontiguousarray(np.stack([np.asarray(o[3], dtype=np.float64) for o in odom]))
+        dcov = np.ascontiguousarray(np.stack([np.asarray(o[4], dtype=np.float64).reshape(self.n * self.n) for o in odom]))
+        ident = np.zeros(self.ps)
+        if self.d == 3:
+            ident[[0, 4, 8]] = 1.0
+        else:
+            ident[0] = 1.0
+        init = np.ascontiguousarray(np.stack([self.values.get(int(o[1]), ident) for o in odom]))
+        self.nfg_odom.extend(o[0] for o in odom)
+        self._check(self.lib.rpgo_odom_append(self.h, n, prev.ctypes.data_as(_capi.c_u64p), new.ctypes.data_as(_capi.c_u64p),
+                                              _dp(dpose), _dp(dcov), _dp(init)), "rpgo_odom_append")
+
+    def _lc_append(self, lcs):
+        # Pcm.h:431-435: both keys must exist in the values
+        lcs = [l for l in lcs if l[1] in self.values and l[2] in self.values]
+        num_new = {}
+        if not lcs:
+            return num_new
+        n = len(lcs)
+        kf = np.array([l[1] for l in lcs], dtype=np.uint64)
+        kt = np.array([l[2] for l in lcs], dtype=np.uint64)
+        pose = np.ascontiguousarray(np.stack([np.asarray(l[3], dtype=np.float64) for l in lcs]))
+        cov = np.ascontiguousarray(np.stack([np.asarray(l[4], dtype=np.float64).reshape(self.n * self.n) for l in lcs]))
+        acc = np.zeros(n, dtype=np.uint8)
+        grp = np.zeros(n, dtype=np.int32)
+        idx = np.zeros(n, dtype=np.int32)
+        self._check(self.lib.rpgo_lc_append(self.h, n, kf.ctypes.data_as(_capi.c_u64p), kt.ctypes.data_as(_capi.c_u64p),
+                                            _dp(pose), _dp(cov), acc.ctypes.data_as(_capi.c_u8p),
+                                            grp.ctypes.data_as(_capi.c_i32p), idx.ctypes.data_as(_capi.c_i32p), None),
+                    "rpgo_lc_append")
+        for i, l in enumerate(lcs):
+            if not acc[i]:
+                continue
+            g = int(grp[i])
+            if g not in self.group_factors:
+                self.group_factors[g] = []
+                self.group_consistent[g] = []
+                self.group_order.append(g)
+            assert len(self.group_factors[g]) == int(idx[i])
+            self.group_factors[g].append(l[0])
+            self.lc_in_order.append(g)
+            self.total_lc += 1
+            num_new[g] = num_new.get(g, 0) + 1
+        return num_new
+
+    def find_inliers_raw(self, g, clique_mode=CLIQUE_HEU, n_new=0, prev_size=0):
+        """(size, ids, true_clique) straight from rpgo_find_inliers."""
+        n = len(self.group_factors[g])
+        ids = np.zeros(max(n, 1), dtype=np.int32)
+        true = np.zeros(max(n, 1), dtype=np.int32)
+        size = C.c_int64(0)
+        self._check(self.lib.rpgo_find_inliers(self.h, g, clique_mode, n_new, prev_size, ids.ctypes.data_as(_capi.c_i32p),
+                                               C.byref(size), true.ctypes.data_as(_capi.c_i32p)), "rpgo_find_inliers")
+        k = int(size.value)
+        return k, ids[:max(k, 0)].copy(), true[:max(k, 0)].copy()
+
+    def _find_inliers(self):  # Pcm.h:851-899
+        self.total_good_lc = 0
+        for g in self.group_order:
+            fs = self.group_factors[g]
+            if self.loop_check:
+                if len(fs) == 0:
+                    self.group_consistent[g] = []
+                    continue
+                k, ids, _ = self.find_inliers_raw(g, CLIQUE_HEU)
+                self.group_consistent[g] = [fs[i] for i in ids[:k]]
+            else:
+                self.group_consistent[g] = list(fs)
+            self.total_good_lc += len(self.group_consistent[g])
+
+    def _find_inliers_incremental(self, num_new):  # Pcm.h:906-970
+        for g, nn in num_new.items():
+            fs = self.group_factors[g]
+            prev = len(self.group_consistent[g])
+            k, ids, _ = self.find_inliers_raw(g, CLIQUE_HEU_INCREMENTAL, nn, prev)
+            if k > 0:
+                self.group_consistent[g] = [fs[i] for i in ids[:k]]
+        self.total_good_lc = sum(len(v) for v in self.group_consistent.values())
+
+    def _group_ids(self, g):
+        a, b, _ = self.group_info(g)
+        return a, b
+
+    def _build_graph(self):  # Pcm.h:977-1005
+        out = list(self.nfg_odom) + list(self.nfg_special)
+        for g in self.group_order:
+            a, b = self._group_ids(g)
+            if ord(a) in self.ignored or ord(b) in self.ignored:
+                continue
+            out.extend(self.group_consistent[g])
+        self.output = out
+
+    # ---- the rest of the OutlierRemoval interface ----------------------------------------------
+    def remove_last(self, c1=None, c2=None):  # Pcm.h:299-353
+        if c1 is None:
+            if not self.lc_in_order:
+                return None
+            g = self.lc_in_order.pop()
+        else:
+            g = self.lib.rpgo_find_group(self.h, ord(c1), ord(c2))
+            if g < 0 or g not in self.group_factors:
+                return None
+        fs = self.group_factors[g]
+        if len(fs) == 0:
+            return None
+        k1, k2 = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.rpgo_lc_remove_last(self.h, g, C.byref(k1), C.byref(k2)), "rpgo_lc_remove_last")
+        fs.pop()
+        if len(fs) < 2:
+            self.group_consistent[g] = list(fs)
+        else:
+            k, ids, _ = self.find_inliers_raw(g, CLIQUE_HEU)
+            self.group_consistent[g] = [fs[i] for i in ids[:k]]
+        self._build_graph()
+        return (k1.value, k2.value)
+
+    def ignore_prefix(self, c):  # Pcm.h:357-365
+        if ord(c) not in self.ignored:
+            self.ignored.append(ord(c))
+        self._build_graph()
+
+    def revive_prefix(self, c):  # Pcm.h:369-377
+        self.ignored = [x for x in self.ignored if x != ord(c)]
+        self._build_graph()
+
+    def get_ignored_prefixes(self):
+        return [chr(x) for x in self.ignored]
+
+    def remove_prior_factors_with_prefix(self, c):  # Pcm.h:387-408
+        self.nfg_special = [f for f in self.nfg_special
+                            if not (f in self.special_is_prior and key_chr(self.special_is_prior[f]) == ord(c))]
+        self._build_graph()
+
+    # counters: OutlierRemoval.h:24-27
+    def num_lc(self):
+        return self.total_lc
+
+    def num_inliers(self):
+        return self.total_good_lc
+
+    def num_odom(self):
+        return len(self.nfg_odom)
+
+    def num_special(self):
+        return len(self.nfg_special)
+
+    def nfg_size(self):
+        return len(self.output)
+
+    def output_ids(self):
+        return np.array(self.output, dtype=np.int64)
+
+    def num_values(self):
+        return len(self.values)
+
+    # ---- inspection (parity) ---------------------------------------------------------------------
+    def group_info(self, g):
+        a, b, n = C.c_uint8(), C.c_uint8(), C.c_int64()
+        self._check(self.lib.rpgo_group_info(self.h, g, C.byref(a), C.byref(b), C.byref(n)), "rpgo_group_info")
+        return chr(a.value), chr(b.value), n.value
+
+    def groups(self):
+        out = []
+        for g in range(self.lib.rpgo_num_groups(self.h)):
+            a, b, n = self.group_info(g)
+            out.append((a, b, n, len(self.group_consistent.get(g, []))))
+        return out
+
+    def group_adj(self, g, with_dist=True):
+        _, _, n = self.group_info(g)
+        sw = max((n + 63) // 64, 1)
+        rows = np.zeros((max(n, 1), sw), dtype=np.uint64)
+        self._check(self.lib.rpgo_adj_bits(self.h, g, rows.ctypes.data_as(_capi.c_u64p), sw), "rpgo_adj_bits")
+        adj = np.unpackbits(rows[:n].view(np.uint8), axis=1, bitorder="little")[:, :n]
+        dist = None
+        if with_dist:
+            dist = np.zeros((n, n))
+            if n > 0:
+                self._check(self.lib.rpgo_pair_distances(self.h, g, _dp(dist)), "rpgo_pair_distances")
+        return adj, dist
+
+    def group_bits(self, g):
+        """raw bitset rows (n x ceil(n/64) uint64)"""
+        _, _, n = self.group_info(g)
+        sw = max((n + 63) // 64, 1)
+        rows = np.zeros((max(n, 1), sw), dtype=np.uint64)
+        self._check(self.lib.rpgo_adj_bits(self.h, g, rows.ctypes.data_as(_capi.c_u64p), sw), "rpgo_adj_bits")
+        return rows[:n]
+
+    def group_factor_ids(self, g):
+        return np.array(self.group_factors[g], dtype=np.int64)
+
+    def group_inlier_ids(self, g):
+        return np.array(self.group_consistent[g], dtype=np.int64)
+
+    def degrees(self, g):
+        _, _, n = self.group_info(g)
+        deg = np.zeros(max(n, 1), dtype=np.int32)
+        self._check(self.lib.rpgo_degrees(self.h, g, deg.ctypes.data_as(_capi.c_i32p)), "rpgo_degrees")
+        return deg[:n]
+
+    def flagged(self, g, cap=4096):
+        pairs = np.zeros((cap, 2), dtype=np.int32)
+        n = C.c_int64()
+        self._check(self.lib.rpgo_near_threshold(self.h, g, pairs.ctypes.data_as(_capi.c_i32p), cap, C.byref(n)),
+                    "rpgo_near_threshold")
+        return n.value, pairs[:min(n.value, cap)]
+
+    def traj_get(self, key):
+        pose = np.zeros(self.ps)
+        cov = np.zeros((self.n, self.n))
+        node, rot = C.c_int32(), C.c_int32()
+        rc = self.lib.rpgo_traj_get(self.h, int(key), _dp(pose), _dp(cov), C.byref(node), C.byref(rot))
+        if rc != 0:
+            return None
+        return pose, cov, node.value, rot.value
+
+    def load_adjacency(self, adj, c1='y', c2='z'):
+        """test/benchmark hook: install a dense 0/1 adjacency as a group; returns the group ordinal."""
+        adj = np.ascontiguousarray(adj, dtype=np.uint8)
+        n = adj.shape[0]
+        sw = max((n + 63) // 64, 1)
+        packed = np.zeros((max(n, 1), sw * 8), dtype=np.uint8)
+        if n:
+            pb = np.packbits(adj, axis=1, bitorder="little")
+            packed[:n, :pb.shape[1]] = pb
+        rows = packed.view(np.uint64)
+        g = C.c_int32(-1)
+        self._check(self.lib.rpgo_debug_load_group(self.h, ord(c1), ord(c2), n, rows.ctypes.data_as(_capi.c_u64p), sw,
+                                                   C.byref(g)), "rpgo_debug_load_group")
+        self.group_factors[g.value] = list(range(n))
+        self.group_consistent.setdefault(g.value, [])
+        if g.value not in self.group_order:
+            self.group_order.append(g.value)
+        return g.value
+
+    def launch_count(self):
+        return int(self.lib.rpgo_launch_count(self.h))
+
+    def sync(self):
+        self._check(self.lib.rpgo_sync(self.h), "rpgo_sync")
+
+    def stream_ptr(self):
+        return self.lib.rpgo_stream(self.h)
+
+    def recompute(self, g, j_begin=0):
+        self._check(self.lib.rpgo_group_recompute(self.h, g, j_begin), "rpgo_group_recompute")

@@ -1,0 +1,56 @@
+// Host-side instantiation of the PRODUCT's math header (kimera-rpgo_b200/csrc/rpgo_math.cuh) so that the
+// CPU test-suite can prove, without a GPU, that its block-structured arithmetic is bit-identical to the
+// dense oracle.  Built by tests/test_cpu_math_parity.py with g++ -ffp-contract=off.
+#include "rpgo_math.cuh"
+
+using namespace rpgo;
+
+template <int D, int MODE>
+static int pair_t(const double* Ta, const double* Tb, const double* lci, const double* Tc, const double* Td,
+                  const double* lcj, const double* thr, double* dist, int* near) {
+  Thresholds th;
+  th.odom = thr[0]; th.lc = thr[1]; th.odom_trans = thr[2]; th.odom_rot = thr[3]; th.dist_trans = thr[4];
+  th.dist_rot = thr[5]; th.band = 1e-9;
+  bool nr;
+  const bool ok = pair_check<D, MODE>(Ta, 1, Tb, 1, lci, 1, Tc, 1, Td, 1, lcj, 1, th, dist, &nr);
+  *near = nr;
+  return ok;
+}
+template <int D, int MODE>
+static void compose_t(const double* a, const double* b, double* o) {
+  PoseT<D, MODE> x, y, z;
+  load_entry<D, MODE>(a, 1, x); load_entry<D, MODE>(b, 1, y);
+  pt_compose<D, MODE>(x, y, z);
+  store_entry<D, MODE>(o, 1, z);
+}
+template <int D, int MODE>
+static void between_t(const double* a, const double* b, double* o) {
+  PoseT<D, MODE> x, y, z;
+  load_entry<D, MODE>(a, 1, x); load_entry<D, MODE>(b, 1, y);
+  pt_between<D, MODE>(x, y, z);
+  store_entry<D, MODE>(o, 1, z);
+}
+template <int D, int MODE>
+static void factor_t(const double* pose, const double* cov, double* o) {
+  PoseT<D, MODE> x;
+  from_factor<D, MODE>(pose, cov, x);
+  for (int i = 0; i < Dim<D>::ENTRY; ++i) o[i] = 0.0;
+  store_entry<D, MODE>(o, 1, x);
+}
+
+#define DISPATCH(d, m, F, ...)                                   \
+  ((d) == 3 ? ((m) == 0 ? F<3, 0>(__VA_ARGS__) : F<3, 1>(__VA_ARGS__)) \
+            : ((m) == 0 ? F<2, 0>(__VA_ARGS__) : F<2, 1>(__VA_ARGS__)))
+
+extern "C" {
+int shim_entry_size(int d) { return d == 3 ? Dim<3>::ENTRY : Dim<2>::ENTRY; }
+int shim_pair_check(int d, int mode, const double* Ta, const double* Tb, const double* lci, const double* Tc,
+                    const double* Td, const double* lcj, const double* thr, double* dist, int* near) {
+  return DISPATCH(d, mode, pair_t, Ta, Tb, lci, Tc, Td, lcj, thr, dist, near);
+}
+void shim_compose(int d, int mode, const double* a, const double* b, double* o) { DISPATCH(d, mode, compose_t, a, b, o); }
+void shim_between(int d, int mode, const double* a, const double* b, double* o) { DISPATCH(d, mode, between_t, a, b, o); }
+void shim_from_factor(int d, int mode, const double* pose, const double* cov, double* o) {
+  DISPATCH(d, mode, factor_t, pose, cov, o);
+}
+}

@@ -1,0 +1,130 @@
+"""CPU-only: the product's block-structured math header, compiled for the host, must agree BIT FOR BIT
+with the dense oracle on random inputs (this pins the summation order the CUDA kernels use)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import orc
+from orc import dp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "tests", "_cpu_math_shim.so")
+
+
+@pytest.fixture(scope="module")
+def shim():
+    src = os.path.join(ROOT, "tests", "cpu_math_shim.cpp")
+    hdr = os.path.join(ROOT, "kimera-rpgo_b200", "csrc", "rpgo_math.cuh")
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        fma = ["-mfma"] if "fma" in open("/proc/cpuinfo").read() else []
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++"] + fma +
+                              ["-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "kimera-rpgo_b200", "csrc"),
+                               src, "-o", SO, "-lm"])
+    L = C.CDLL(SO)
+    L.shim_entry_size.restype = C.c_int
+    L.shim_pair_check.restype = C.c_int
+    return L
+
+
+def rand_pose(rng, d, scale=5.0):
+    if d == 3:
+        q = rng.normal(size=4)
+        R = orc.quat_R(*q)
+        return orc.pose3(R, rng.uniform(-scale, scale, size=3))
+    th = rng.uniform(-np.pi, np.pi)
+    return orc.pose2(th, rng.uniform(-scale, scale, size=2))
+
+
+def rand_cov(rng, n, scale):
+    a = rng.normal(size=(n, n))
+    return scale * (a @ a.T / n + 0.05 * np.eye(n))
+
+
+def entry(L, d, pose, cov, rot=1, node=0):
+    E = L.shim_entry_size(d)
+    e = np.zeros(E)
+    ps, n = orc.psize(d), orc.ndim(d)
+    e[:ps] = pose
+    oc = 12 if d == 3 else 4
+    e[oc:oc + n * n] = np.asarray(cov).reshape(-1)
+    e[48 if d == 3 else 13] = rot
+    e[49 if d == 3 else 14] = node
+    return e
+
+
+@pytest.mark.parametrize("d", [3, 2])
+def test_compose_between_bitwise(shim, d):
+    rng = np.random.default_rng(100 + d)
+    n = orc.ndim(d)
+    E = shim.shim_entry_size(d)
+    oc = 12 if d == 3 else 4
+    for t in range(300):
+        pa, pb = rand_pose(rng, d), rand_pose(rng, d)
+        ca, cb = rand_cov(rng, n, 0.01), rand_cov(rng, n, 0.01)
+        if t % 2:
+            cb = ca + rand_cov(rng, n, 0.001)  # exercise both LLT outcomes
+        out = np.zeros(E)
+        shim.shim_compose(d, 0, dp(entry(shim, d, pa, ca)), dp(entry(shim, d, pb, cb)), dp(out))
+        po, co, _ = orc.pwc_compose(d, (pa, ca, 1), (pb, cb, 1))
+        assert np.array_equal(out[:orc.psize(d)], po) and np.array_equal(out[oc:oc + n * n].reshape(n, n), co), t
+        shim.shim_between(d, 0, dp(entry(shim, d, pa, ca)), dp(entry(shim, d, pb, cb)), dp(out))
+        po, co, _ = orc.pwc_between(d, (pa, ca, 1), (pb, cb, 1))
+        assert np.array_equal(out[:orc.psize(d)], po) and np.array_equal(out[oc:oc + n * n].reshape(n, n), co), t
+
+
+@pytest.mark.parametrize("d", [3, 2])
+def test_pair_check_pcm_bitwise(shim, d):
+    """areLoopsConsistent chain (Pcm.h:703-717) + mahalanobis: product header == oracle, bit for bit."""
+    rng = np.random.default_rng(200 + d)
+    n = orc.ndim(d)
+    thr = np.array([1.0, 3.0, 1, 1, 1, 1.0])
+    for t in range(400):
+        P = [rand_pose(rng, d, 3.0) for _ in range(6)]
+        Ccum = [rand_cov(rng, n, 0.02) for _ in range(2)]
+        # trajectory covariances: later = earlier + something (PSD difference) or the other way round
+        Ta = (P[0], Ccum[0], 1); Tc = (P[1], Ccum[0] + (1 if t % 2 else -0.5) * rand_cov(rng, n, 0.004), 1)
+        Tb = (P[2], Ccum[1], 1); Td = (P[3], Ccum[1] + (1 if t % 3 else -0.5) * rand_cov(rng, n, 0.004), 1)
+        rot_i = 0 if t % 11 == 0 else 1
+        lci = (P[4], rand_cov(rng, n, 0.01), rot_i); lcj = (P[5], rand_cov(rng, n, 0.01), 1)
+        # oracle chain
+        a_odom_c = orc.pwc_between(d, Ta, Tc)
+        b_odom_d = orc.pwc_between(d, Tb, Td)
+        a_path_d = orc.pwc_compose(d, a_odom_c, lcj)
+        d_path_b = orc.pwc_compose(d, orc.pwc_inverse(d, a_path_d), lci)
+        loop = orc.pwc_compose(d, d_path_b, b_odom_d)
+        want = orc.pwc_mahalanobis(d, loop)
+        dist = C.c_double(); near = C.c_int()
+        E = [entry(shim, d, *x) for x in (Ta, Tb, lci, Tc, Td, lcj)]
+        ok = shim.shim_pair_check(d, 0, *[dp(e) for e in E], dp(thr), C.byref(dist), C.byref(near))
+        assert (dist.value == want) or (np.isnan(dist.value) and np.isnan(want)), (t, dist.value, want)
+        assert bool(ok) == bool(want < thr[1])
+
+
+@pytest.mark.parametrize("d", [3, 2])
+def test_pair_check_simple_bitwise(shim, d):
+    rng = np.random.default_rng(300 + d)
+    n = orc.ndim(d)
+    L = orc.lib()
+    thr = np.array([1.0, 3.0, 1, 1, 0.05, 0.01])
+    for t in range(300):
+        P = [rand_pose(rng, d, 1.0) for _ in range(6)]
+        nodes = rng.integers(0, 50, size=4)
+        # oracle via its pose primitives
+        btw = lambda a, b: orc.pose_compose(d, orc.pose_inverse(d, a), b)
+        a_odom_c, nac = btw(P[0], P[1]), abs(int(nodes[1]) - int(nodes[0]))
+        b_odom_d, nbd = btw(P[2], P[3]), abs(int(nodes[3]) - int(nodes[2]))
+        a_path_d = orc.pose_compose(d, a_odom_c, P[5])
+        d_path_b = orc.pose_compose(d, orc.pose_inverse(d, a_path_d), P[4])
+        loop = orc.pose_compose(d, d_path_b, b_odom_d)
+        node = nac + 1 + 1 + nbd
+        wt, wr = orc.pwn_norms(d, loop, node)
+        dist = C.c_double(); near = C.c_int()
+        z = np.zeros((n, n))
+        E = [entry(shim, d, P[0], z, 1, nodes[0]), entry(shim, d, P[2], z, 1, nodes[2]), entry(shim, d, P[4], z, 1, 1),
+             entry(shim, d, P[1], z, 1, nodes[1]), entry(shim, d, P[3], z, 1, nodes[3]), entry(shim, d, P[5], z, 1, 1)]
+        ok = shim.shim_pair_check(d, 1, *[dp(e) for e in E], dp(thr), C.byref(dist), C.byref(near))
+        assert dist.value == wt, (t, dist.value, wt)
+        assert bool(ok) == bool(wt < thr[4] and wr < thr[5])
