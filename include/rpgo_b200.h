@@ -150,6 +150,8 @@ int rpgo_pair_distances(rpgo_handle* h, int32_t g, double* dist_out);
  * Re-run the pairwise kernel over columns [j_begin, n) of group g from the device-resident tables
  * (inputs already in HBM; same launch rpgo_lc_append issues).  Used by bench.py for kernel-only timing. */
 int rpgo_group_recompute(rpgo_handle* h, int32_t g, int64_t j_begin);
+/* the pairwise kernel alone (no mirror / degree pass): what roofline.achieved is measured on */
+int rpgo_group_pairwise(rpgo_handle* h, int32_t g, int64_t j_begin);
 /* multi-GPU: after the caller has all-gathered the upper-triangle row chunks, rebuild the lower
  * triangle and the degrees on this GPU */
 int rpgo_group_finalize(rpgo_handle* h, int32_t g);

@@ -48,6 +48,7 @@ SYMBOLS = [
     ("rpgo_near_threshold", C.c_int, [C.c_void_p, C.c_int32, c_i32p, C.c_int64, c_i64p]),
     ("rpgo_pair_distances", C.c_int, [C.c_void_p, C.c_int32, c_dp]),
     ("rpgo_group_recompute", C.c_int, [C.c_void_p, C.c_int32, C.c_int64]),
+    ("rpgo_group_pairwise", C.c_int, [C.c_void_p, C.c_int32, C.c_int64]),
     ("rpgo_group_finalize", C.c_int, [C.c_void_p, C.c_int32]),
     ("rpgo_group_chunking", C.c_int, [C.c_void_p, C.c_int32, c_i64p, c_i64p]),
     ("rpgo_launch_count", C.c_int64, [C.c_void_p]),

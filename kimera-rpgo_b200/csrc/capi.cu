@@ -82,6 +82,8 @@ struct Group {
   int64_t cap = 0;       /* capacity in closures (multiple of 128) */
   int64_t stride32 = 0;  /* adjacency row stride in 32-bit words (= cap / 32) */
   DevBuf lc, idxf, idxb, pfx, bits, deg, fl_pairs, fl_count;
+  DevBuf rec_aos, rec_soa; /* gathered per-closure records for the tiled kernel */
+  int64_t gathered = 0;    /* closures [0, gathered) have up-to-date records */
   std::vector<uint64_t> kfrom, kto;
   std::vector<int32_t> h_idxf, h_idxb;
   std::vector<uint8_t> h_pfx;
@@ -105,6 +107,8 @@ struct rpgo_handle {
   int64_t traj_n = 0;
   std::unordered_map<uint64_t, int32_t> key2idx;
   std::set<uint8_t> prefixes; /* prefixes for which odom_trajectories_ has an entry */
+  std::set<uint64_t> missing_refs; /* keys looked up by a closure while absent (default entry used) */
+  bool traj_dirty = false;         /* an entry a stored closure refers to has changed since it was resolved */
 
   std::vector<Group*> groups;
   std::map<std::pair<uint8_t, uint8_t>, int32_t> gindex;
@@ -177,6 +181,11 @@ static int ensure_group(rpgo_handle* h, Group* g, int64_t need) {
   H_CHECK_CUDA(h, g->idxb.ensure((size_t)ncap * 4, (size_t)g->n * 4, st));
   H_CHECK_CUDA(h, g->pfx.ensure((size_t)ncap, (size_t)g->n, st));
   H_CHECK_CUDA(h, g->deg.ensure((size_t)ncap * 4, 0, st));
+  if (h->loop_check && h->mode == MODE_PCM) {
+    const size_t rn = (size_t)tiled_record_doubles(h->dim) * 8;
+    H_CHECK_CUDA(h, g->rec_aos.ensure((size_t)ncap * rn + 256, (size_t)g->n * rn, st));
+    H_CHECK_CUDA(h, g->rec_soa.ensure((size_t)ncap * rn + 256, (size_t)((g->n + 31) / 32) * 32 * rn, st));
+  }
   if (h->loop_check) {
     /* adjacency: ncap rows x ncap/32 words; the row pitch changes, so copy row by row (2D copy) */
     const int64_t nstride = ncap / 32;
@@ -218,12 +227,24 @@ static int run_pairwise(rpgo_handle* h, Group* g, int64_t j_begin, double* dist_
   GroupView v = group_view(h, g);
   Shard sh = group_shard(h, g);
   int kernel = h->cfg.kernel;
+  {
+    extern int g_direct_minb_set(int);
+    g_direct_minb_set(kernel == 13 ? 3 : kernel == 14 ? 4 : 2);
+    if (kernel == 13 || kernel == 14) kernel = RPGO_KERNEL_DIRECT;
+  }
   if (dist_dev) kernel = RPGO_KERNEL_DIRECT;
-  if (kernel == RPGO_KERNEL_AUTO) kernel = RPGO_KERNEL_DIRECT;
-  if (kernel == RPGO_KERNEL_TILED && !(h->dim == 3 && h->mode == MODE_PCM)) kernel = RPGO_KERNEL_DIRECT;
-  if (kernel == RPGO_KERNEL_TILED)
-    launch_pairwise_tiled(h->dim, h->mode, v, h->traj.as<double>(), (int)j_begin, sh, h->th, group_flagged(g), h->stream);
-  else
+  if (kernel == RPGO_KERNEL_AUTO) kernel = (h->mode == MODE_PCM) ? RPGO_KERNEL_TILED : RPGO_KERNEL_DIRECT;
+  if (kernel == RPGO_KERNEL_TILED && h->mode != MODE_PCM) kernel = RPGO_KERNEL_DIRECT;
+  if (kernel == RPGO_KERNEL_TILED) {
+    if (g->gathered < g->n) {
+      launch_gather_records(h->dim, v, h->traj.as<double>(), (int)g->gathered, g->rec_aos.as<double>(), g->rec_soa.as<double>(),
+                            h->stream);
+      g->gathered = g->n;
+      h->launches += 1;
+    }
+    launch_pairwise_tiled(h->dim, h->mode, v, g->rec_aos.as<double>(), g->rec_soa.as<double>(), (int)j_begin, sh, h->th,
+                          group_flagged(g), h->stream);
+  } else
     launch_pairwise_direct(h->dim, h->mode, v, h->traj.as<double>(), (int)j_begin, sh, h->th, group_flagged(g), dist_dev,
                            h->stream);
   h->launches += 1;
@@ -363,8 +384,10 @@ int rpgo_odom_append(rpgo_handle* h, int64_t n, const uint64_t* prev_key, const 
       if (it == h->key2idx.end()) {
         idx = (int32_t)new_entries++;
         h->key2idx[prev_key[k]] = idx;
+        if (h->missing_refs.erase(prev_key[k])) h->traj_dirty = true;
       } else {
         idx = it->second;
+        h->traj_dirty = true;
       }
       seeds.push_back({idx, k});
     }
@@ -374,8 +397,10 @@ int rpgo_odom_append(rpgo_handle* h, int64_t n, const uint64_t* prev_key, const 
     if (it == h->key2idx.end()) {
       out = (int32_t)new_entries++;
       h->key2idx[new_key[k]] = out;
+      if (h->missing_refs.erase(new_key[k])) h->traj_dirty = true; /* a closure resolved this key to the default entry */
     } else {
       out = it->second;
+      h->traj_dirty = true; /* poses[new_key] overwritten (Pcm.h:556) */
     }
     auto oc = open_chain.find(prefix);
     if (oc != open_chain.end() && chain_tail_key[oc->second] == prev_key[k]) {
@@ -518,6 +543,23 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
   const int E = h->E, PS = h->PS, NN = h->NN;
   cudaStream_t st = h->stream;
 
+  if (h->traj_dirty) {
+    /* the reference looks trajectory entries up at every pair check (GraphUtils.h:40-42), so closures
+     * stored earlier must see entries that appeared / changed since: re-resolve and re-gather */
+    for (Group* g : h->groups) {
+      for (int64_t k = 0; k < g->n; ++k) {
+        g->h_idxf[k] = traj_lookup(h, g->kfrom[k]);
+        g->h_idxb[k] = traj_lookup(h, g->kto[k]);
+      }
+      if (g->n > 0 && g->idxf.p) {
+        H_CHECK_CUDA(h, cudaMemcpyAsync(g->idxf.p, g->h_idxf.data(), (size_t)g->n * 4, cudaMemcpyHostToDevice, st));
+        H_CHECK_CUDA(h, cudaMemcpyAsync(g->idxb.p, g->h_idxb.data(), (size_t)g->n * 4, cudaMemcpyHostToDevice, st));
+      }
+      g->gathered = 0;
+    }
+    H_CHECK_CUDA(h, cudaStreamSynchronize(st));
+    h->traj_dirty = false;
+  }
   /* stage inputs: pose | cov | idxf | idxb | check */
   const size_t o_cov = (size_t)n * PS * 8, o_if = o_cov + (size_t)n * NN * 8, o_ib = o_if + (size_t)n * 4,
                o_ck = o_ib + (size_t)n * 4, o_dst = (o_ck + (size_t)n + 15) & ~size_t(15),
@@ -537,6 +579,8 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
     if (p_ck[k]) h->prefixes.insert(cf); /* odom_trajectories_[chr] is created by the lookup, Pcm.h:619 */
     p_if[k] = traj_lookup(h, key_from[k]);
     p_ib[k] = traj_lookup(h, key_to[k]);
+    if (p_if[k] == 0 && !h->key2idx.count(key_from[k])) h->missing_refs.insert(key_from[k]);
+    if (p_ib[k] == 0 && !h->key2idx.count(key_to[k])) h->missing_refs.insert(key_to[k]);
   }
   H_CHECK_CUDA(h, h->d_stage.ensure(total, 0, st));
   H_CHECK_CUDA(h, h->d_lcent.ensure((size_t)n * E * 8, 0, st));
@@ -680,6 +724,7 @@ int rpgo_lc_remove_last(rpgo_handle* h, int32_t gi, uint64_t* key_from, uint64_t
   g->h_idxb.pop_back();
   g->h_pfx.pop_back();
   g->n -= 1;
+  if (g->gathered > g->n) g->gathered = g->n;
   if (h->loop_check && g->bits.p) {
     launch_clear_last(g->bits.as<uint32_t>(), g->stride32, (int)g->n, h->stream);
     launch_degree(g->bits.as<uint32_t>(), g->stride32, (int)g->n, g->deg.as<int32_t>(), h->stream);
@@ -826,6 +871,15 @@ int rpgo_group_recompute(rpgo_handle* h, int32_t gi, int64_t j_begin) {
   return rc;
 }
 
+int rpgo_group_pairwise(rpgo_handle* h, int32_t gi, int64_t j_begin) {
+  if (!h) return RPGO_ERR_INVALID;
+  if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
+  Group* g = h->groups[gi];
+  if (j_begin < 0 || j_begin > g->n) return RPGO_ERR_INVALID;
+  if (g->fl_count.p) H_CHECK_CUDA(h, cudaMemsetAsync(g->fl_count.p, 0, 8, h->stream));
+  return run_pairwise(h, g, j_begin, nullptr);
+}
+
 int rpgo_group_finalize(rpgo_handle* h, int32_t gi) {
   if (!h) return RPGO_ERR_INVALID;
   if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
@@ -867,6 +921,7 @@ int rpgo_debug_load_group(rpgo_handle* h, uint8_t id1, uint8_t id2, int64_t n, c
     H_CHECK_CUDA(h, cudaMemcpy2DAsync(g->bits.p, (size_t)g->stride32 * 4, rows, (size_t)stride_words * 8,
                                       (size_t)((n + 31) / 32) * 4, (size_t)n, cudaMemcpyHostToDevice, h->stream));
   g->n = n;
+  g->gathered = 0;
   g->kfrom.assign((size_t)n, 0);
   g->kto.assign((size_t)n, 0);
   g->h_idxf.assign((size_t)n, 0);

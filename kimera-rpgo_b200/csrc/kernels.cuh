@@ -57,8 +57,10 @@ void launch_scatter_entries(int dim, int n, const double* entries, const uint64_
 /* K3 */
 void launch_pairwise_direct(int dim, int mode, GroupView g, const double* traj, int j_begin, Shard sh, Thresholds th,
                             Flagged fl, double* dist_out, cudaStream_t st);
-void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* traj, int j_begin, Shard sh, Thresholds th,
-                           Flagged fl, cudaStream_t st);
+int tiled_record_doubles(int dim);
+void launch_gather_records(int dim, GroupView g, const double* traj, int k0, double* aos, double* soa, cudaStream_t st);
+void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, const double* soa, int j_begin, Shard sh,
+                           Thresholds th, Flagged fl, cudaStream_t st);
 /* bitset maintenance */
 void launch_mirror(uint32_t* bits, int64_t stride32, int n, int j_begin, cudaStream_t st);
 void launch_degree(const uint32_t* bits, int64_t stride32, int n, int32_t* deg, cudaStream_t st);

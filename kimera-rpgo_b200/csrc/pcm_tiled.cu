@@ -1,8 +1,216 @@
-/* pcm_tiled.cu — K3, TMA-staged shared-memory tiled variant (placeholder: forwards to the direct kernel). */
+/* pcm_tiled.cu — K3, the pairwise consistency kernel, TMA-staged shared-memory variant (sm_100a).
+ *
+ * Replaces Pcm::incrementAdjMatrix + areLoopsConsistent (reference Pcm.h:670-768) for one
+ * ObservationId group.  Work decomposition:
+ *   - a gather pass packs, per closure, everything a pair check needs into one record
+ *       [ T(key_from) | T(key_to) | T(closure) | prefix ]   (3*ENTRY+2 doubles)
+ *     twice: array-of-structs (rows: the OLDER closure i, warp-uniform, read as broadcasts) and
+ *     struct-of-arrays in slabs of 32 closures (columns: the NEWER closure j, one per lane, read
+ *     conflict-free);
+ *   - a thread block owns one slab of 32 columns and a segment of rows.  The column slab (38 KB) is
+ *     brought in by ONE bulk TMA copy (cp.async.bulk ... mbarrier::complete_tx) and stays resident;
+ *     the row records stream through a 2-stage TMA/mbarrier pipeline, 4 rows (one per warp) at a time;
+ *   - one thread evaluates one pair with pair_check_v1 (single running covariance in registers,
+ *     b_odom_d parked in a per-thread shared-memory scratch column); the 32 decisions of a warp are
+ *     packed by __ballot_sync into the adjacency word (i, j/32).
+ * FP64 CUDA-core bound by design (6x6 / 3x3 fp64 with data-dependent branches: no tensor cores).
+ */
+#include <cstdio>
+
 #include "kernels.cuh"
+
 namespace rpgo {
-void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* traj, int j_begin, Shard sh, Thresholds th,
-                           Flagged fl, cudaStream_t st) {
-  launch_pairwise_direct(dim, mode, g, traj, j_begin, sh, th, fl, nullptr, st);
+
+template <int D>
+struct Rec {
+  static constexpr int E = Dim<D>::ENTRY;
+  static constexpr int N = 3 * E + 2; /* doubles per record (16-byte multiple) */
+  static constexpr int OFF_TF = 0, OFF_TB = E, OFF_LC = 2 * E, OFF_PFX = 3 * E;
+};
+
+int tiled_record_doubles(int dim) { return dim == 3 ? Rec<3>::N : Rec<2>::N; }
+
+/* ---- gather -------------------------------------------------------------------------------------- */
+template <int D>
+__global__ void gather_records_kernel(GroupView g, const double* __restrict__ traj, int k0, double* aos, double* soa) {
+  constexpr int E = Rec<D>::E, RN = Rec<D>::N;
+  const int k = k0 + blockIdx.x;
+  if (k >= g.n) return;
+  for (int f = threadIdx.x; f < RN; f += blockDim.x) {
+    double v = 0.0;
+    if (f < E) v = traj[(size_t)g.idx_front[k] * E + f];
+    else if (f < 2 * E) v = traj[(size_t)g.idx_back[k] * E + (f - E)];
+    else if (f < 3 * E) v = g.lc[(size_t)k * E + (f - 2 * E)];
+    else if (f == 3 * E) v = (double)g.pfx_front[k];
+    aos[(size_t)k * RN + f] = v;
+    soa[((size_t)(k >> 5) * RN + f) * 32 + (k & 31)] = v;
+  }
 }
+
+/* ---- PTX helpers: mbarrier + 1-D bulk TMA ------------------------------------------------------------ */
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ bool row_owned_t(const Shard& sh, int i) {
+  if (sh.world <= 1) return true;
+  const int64_t c = i / sh.chunk_rows;
+  return c == sh.rank || c == 2 * (int64_t)sh.world - 1 - sh.rank;
+}
+
+constexpr int TILE_WARPS = 4;   /* rows per pipeline stage (one per warp) */
+constexpr int TILE_SEG = 512;   /* rows per work item */
+
+template <int D>
+struct TiledSmem {
+  static constexpr int RN = Rec<D>::N, E = Rec<D>::E;
+  static constexpr size_t JT = (size_t)RN * 32 * 8;                 /* column slab */
+  static constexpr size_t IT = (size_t)2 * TILE_WARPS * RN * 8;     /* 2 stages of row records */
+  static constexpr size_t SCR = (size_t)E * TILE_WARPS * 32 * 8;    /* per-thread scratch entry */
+  static constexpr size_t BYTES = JT + IT + SCR + 64;
+};
+
+template <int D>
+__global__ void __launch_bounds__(TILE_WARPS * 32, 2)
+    pairwise_tiled_kernel(GroupView g, const double* __restrict__ aos, const double* __restrict__ soa, int j_begin,
+                          int cb_begin, Shard sh, Thresholds th, Flagged fl) {
+  constexpr int RN = Rec<D>::N, E = Rec<D>::E;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* Jt = reinterpret_cast<double*>(smem_raw);
+  double* It = reinterpret_cast<double*>(smem_raw + TiledSmem<D>::JT);
+  double* Scr = reinterpret_cast<double*>(smem_raw + TiledSmem<D>::JT + TiledSmem<D>::IT);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TiledSmem<D>::JT + TiledSmem<D>::IT + TiledSmem<D>::SCR);
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int cb = cb_begin + blockIdx.y;          /* column slab */
+  const int r0 = blockIdx.x * TILE_SEG;
+  int r_end = min(g.n, cb * 32 + 31);            /* rows i with some j > i in this slab */
+  r_end = min(r_end, r0 + TILE_SEG);
+  if (r0 >= r_end) return;
+  if (sh.world > 1) {
+    /* whole segment inside one foreign chunk: nothing to do */
+    const int64_t c0 = r0 / sh.chunk_rows, c1 = (r_end - 1) / sh.chunk_rows;
+    if (c0 == c1 && !row_owned_t(sh, r0)) return;
+  }
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], (uint32_t)TiledSmem<D>::JT);
+    tma_load_1d(Jt, soa + (size_t)cb * RN * 32, (uint32_t)TiledSmem<D>::JT, &bars[0]);
+    const int rows = min(TILE_WARPS, r_end - r0);
+    mbar_expect_tx(&bars[1], (uint32_t)(rows * RN * 8));
+    tma_load_1d(It, aos + (size_t)r0 * RN, (uint32_t)(rows * RN * 8), &bars[1]);
+  }
+  mbar_wait(&bars[0], 0);
+
+  const int j = cb * 32 + lane;
+  const double* Jl = Jt + lane; /* field f of column j: Jl[f * 32] */
+  const uint8_t pc = (uint8_t)Jl[Rec<D>::OFF_PFX * 32];
+  double* scr = Scr + tid;      /* field f: scr[f * 128] */
+
+  int it = 0;
+  for (int base = r0; base < r_end; base += TILE_WARPS, ++it) {
+    const int stage = it & 1;
+    if (tid == 0 && base + TILE_WARPS < r_end) {
+      const int rows = min(TILE_WARPS, r_end - (base + TILE_WARPS));
+      mbar_expect_tx(&bars[1 + (stage ^ 1)], (uint32_t)(rows * RN * 8));
+      tma_load_1d(It + (size_t)(stage ^ 1) * TILE_WARPS * RN, aos + (size_t)(base + TILE_WARPS) * RN, (uint32_t)(rows * RN * 8),
+                  &bars[1 + (stage ^ 1)]);
+    }
+    mbar_wait(&bars[1 + stage], (uint32_t)((it >> 1) & 1));
+    const int i = base + w;
+    if (i < r_end && row_owned_t(sh, i)) {
+      const double* Ir = It + ((size_t)stage * TILE_WARPS + w) * RN;
+      bool ok = false;
+      if (j < g.n && j > i && j >= j_begin) {
+        const uint8_t pa = (uint8_t)Ir[Rec<D>::OFF_PFX];
+        /* Pcm.h:691-698: if the prefixes of a and c differ, c and d swap (measurement not inverted) */
+        const double* Tc = (pa != pc) ? Jl + Rec<D>::OFF_TB * 32 : Jl + Rec<D>::OFF_TF * 32;
+        const double* Td = (pa != pc) ? Jl + Rec<D>::OFF_TF * 32 : Jl + Rec<D>::OFF_TB * 32;
+        double dist;
+        bool near;
+        ok = pair_check_v1<D>(Ir + Rec<D>::OFF_TF, 1, Ir + Rec<D>::OFF_TB, 1, Ir + Rec<D>::OFF_LC, 1, Tc, 32, Td, 32,
+                              Jl + Rec<D>::OFF_LC * 32, 32, scr, TILE_WARPS * 32, th, &dist, &near);
+        if (near) {
+          const unsigned long long slot = atomicAdd(fl.count, 1ULL);
+          if ((int64_t)slot < fl.cap) {
+            fl.pairs[2 * slot] = i;
+            fl.pairs[2 * slot + 1] = j;
+          }
+        }
+      }
+      const unsigned word = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) {
+        unsigned keep = 0;
+        if (j_begin > cb * 32) keep = (j_begin >= cb * 32 + 32) ? 0xffffffffu : ((1u << (j_begin - cb * 32)) - 1u);
+        uint32_t* p = g.bits + (size_t)i * g.stride32 + cb;
+        *p = (*p & keep) | word;
+      }
+    }
+    __syncthreads(); /* stage buffer is free for the copy issued at the top of the next iteration */
+  }
+}
+
+static void gather_launch(int dim, GroupView g, const double* traj, int k0, double* aos, double* soa, cudaStream_t st) {
+  if (k0 >= g.n) return;
+  if (dim == 3) gather_records_kernel<3><<<g.n - k0, 160, 0, st>>>(g, traj, k0, aos, soa);
+  else gather_records_kernel<2><<<g.n - k0, 64, 0, st>>>(g, traj, k0, aos, soa);
+}
+
+void launch_gather_records(int dim, GroupView g, const double* traj, int k0, double* aos, double* soa, cudaStream_t st) {
+  gather_launch(dim, g, traj, k0, aos, soa, st);
+}
+
+void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, const double* soa, int j_begin, Shard sh,
+                           Thresholds th, Flagged fl, cudaStream_t st) {
+  (void)mode; /* MODE_PCM only */
+  if (g.n < 2 || j_begin >= g.n) return;
+  const int cb_begin = j_begin / 32;
+  const int cb_end = (g.n + 31) / 32;
+  dim3 grid((g.n + TILE_SEG - 1) / TILE_SEG, cb_end - cb_begin);
+  static bool attr3 = false, attr2 = false;
+  if (dim == 3) {
+    if (!attr3) {
+      cudaFuncSetAttribute(pairwise_tiled_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TiledSmem<3>::BYTES);
+      attr3 = true;
+    }
+    pairwise_tiled_kernel<3><<<grid, TILE_WARPS * 32, TiledSmem<3>::BYTES, st>>>(g, aos, soa, j_begin, cb_begin, sh, th, fl);
+  } else {
+    if (!attr2) {
+      cudaFuncSetAttribute(pairwise_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TiledSmem<2>::BYTES);
+      attr2 = true;
+    }
+    pairwise_tiled_kernel<2><<<grid, TILE_WARPS * 32, TiledSmem<2>::BYTES, st>>>(g, aos, soa, j_begin, cb_begin, sh, th, fl);
+  }
+}
+
 }  // namespace rpgo

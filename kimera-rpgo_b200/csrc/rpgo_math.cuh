@@ -275,17 +275,32 @@ RPGO_FN double quad_form_inv(const double* Min, const double* v) {
       if (a > biggest) { biggest = a; piv = i; }
     }
     if (biggest != 0.0) {
+      /* exchange rows k and piv with value selects only (a data-dependent row index would push the
+       * whole matrix into local memory) */
       RPGO_UNROLL
-      for (int i = k + 1; i < N; ++i) {
-        if (piv == i) {
-          RPGO_UNROLL
-          for (int j = 0; j < N; ++j) {
-            const double tmp = lu[k * N + j];
-            lu[k * N + j] = lu[i * N + j];
-            lu[i * N + j] = tmp;
-          }
-          const int tp = perm[k]; perm[k] = perm[i]; perm[i] = tp;
+      for (int j = 0; j < N; ++j) {
+        const double oldk = lu[k * N + j];
+        double newk = oldk;
+        RPGO_UNROLL
+        for (int i = k + 1; i < N; ++i) {
+          const bool sw = (piv == i);
+          const double vi = lu[i * N + j];
+          newk = sw ? vi : newk;
+          lu[i * N + j] = sw ? oldk : vi;
         }
+        lu[k * N + j] = newk;
+      }
+      {
+        const int oldk = perm[k];
+        int newk = oldk;
+        RPGO_UNROLL
+        for (int i = k + 1; i < N; ++i) {
+          const bool sw = (piv == i);
+          const int vi = perm[i];
+          newk = sw ? vi : newk;
+          perm[i] = sw ? oldk : vi;
+        }
+        perm[k] = newk;
       }
       const double pv = lu[k * N + k];
       RPGO_UNROLL
@@ -619,6 +634,114 @@ RPGO_FN bool pair_check(const double* Ta, int sa, const double* Tb, int sb, cons
   }
   pt_compose<D, MODE>(x, y, z); /* loop */
   return check_consistent<D, MODE>(z, th, false, dist, near);
+}
+
+
+/* ------------------------------------------------------------------------------------------------
+ * pair_check_v1: same arithmetic as pair_check (bit-identical results), restructured for the tiled
+ * kernel:
+ *   - both between() stages and all three compose() stages run through ONE loop body each
+ *     (#pragma unroll 1) so the kernel's hot code stays small enough for the instruction cache;
+ *   - between()'s "LLT failed -> recompute the other way round" branch (GeometryUtils.h:150-161) is made
+ *     warp-convergent: LLT fails at pivot 0 iff cov(0,0) <= 0 (no arithmetic precedes that test), so the
+ *     (0,0) element is probed first (21 fused ops) and each lane picks its direction BEFORE the one full
+ *     H S H^T it needs; lanes of both kinds then execute the same instructions on per-lane-selected
+ *     operands.  Only a failure at a later pivot (numerically indefinite input) takes a divergent path;
+ *   - b_odom_d is computed first and parked in `scr` (ENTRY doubles, element stride ss: per-thread
+ *     scratch in shared memory) so that a single running covariance lives in registers.
+ * Only MODE_PCM uses this path.
+ * ---------------------------------------------------------------------------------------------- */
+template <int D>
+RPGO_FN void load_pose(const double* __restrict__ e, int st, Pose<D>& p) {
+  RPGO_UNROLL
+  for (int i = 0; i < Dim<D>::PS; ++i) p.m[i] = e[i * st];
+}
+
+/* (H S H^T)(0,0) with exactly the operations hsht() performs for that element */
+template <int D>
+RPGO_FN double hsht00(const Adj<D>& H, const double* __restrict__ S, int st) {
+  constexpr int N = Dim<D>::N;
+  const double* h = H.h;
+  double t[3];
+  RPGO_UNROLL
+  for (int j = 0; j < 3; ++j) t[j] = dot3(h[0], h[1], h[2], S[(0 * N + j) * st], S[(1 * N + j) * st], S[(2 * N + j) * st]);
+  return dot3(t[0], t[1], t[2], h[0], h[1], h[2]);
+}
+
+template <int D>
+RPGO_FN bool pair_check_v1(const double* Ta, int sa, const double* Tb, int sb, const double* lci, int sli,
+                           const double* Tc, int sc, const double* Td, int sd, const double* lcj, int slj,
+                           double* scr, int ss, const Thresholds& th, double* dist, bool* near) {
+  constexpr int N = Dim<D>::N, NN = N * N, OC = Dim<D>::OFF_COV, OR = Dim<D>::OFF_ROT;
+  PoseT<D, MODE_PCM> x; /* running value of the chain */
+  bool rot_chain = true;
+
+  /* ---- the two between() stages: s = 0: b_odom_d -> scratch, s = 1: a_odom_c -> x ---- */
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int s = 0; s < 2; ++s) {
+    const double* pa = s == 0 ? Tb : Ta;
+    const int sta = s == 0 ? sb : sa;
+    const double* pb = s == 0 ? Td : Tc;
+    const int stb = s == 0 ? sd : sc;
+    Pose<D> A, B;
+    load_pose<D>(pa, sta, A);
+    load_pose<D>(pb, stb, B);
+    const Pose<D> P = between<D>(A, B);                 /* result pose (both directions keep it) */
+    Adj<D> H = adjoint<D>(inverse<D>(P));
+    /* probe: forward covariance element (0,0) = cov_b(0,0) - (H cov_a H^T)(0,0) */
+    const double c00 = pb[OC * stb] - hsht00<D>(H, pa + OC * sta, sta);
+    const bool swapped = c00 <= 0.0;                    /* LLT pivot 0 fails  <=>  recompute the other way */
+    if (swapped) H = adjoint<D>(inverse<D>(between<D>(B, A)));
+    const double* pS = swapped ? pb : pa;               /* covariance that is propagated */
+    const int stS = swapped ? stb : sta;
+    const double* pT = swapped ? pa : pb;               /* covariance it is subtracted from */
+    const int stT = swapped ? sta : stb;
+    double S[NN];
+    RPGO_UNROLL
+    for (int i = 0; i < NN; ++i) S[i] = pS[(OC + i) * stS];
+    hsht<D>(H, [&](int r, int c) { return S[r * N + c]; }, x.cov);
+    RPGO_UNROLL
+    for (int i = 0; i < NN; ++i) x.cov[i] = pT[(OC + i) * stT] - x.cov[i];
+    if (!swapped) {
+      if (!llt_ok<N>(x.cov)) {
+        /* failure at a later pivot: rare, divergent slow path, identical to the reference's order */
+        const Adj<D> H2 = adjoint<D>(inverse<D>(between<D>(B, A)));
+        RPGO_UNROLL
+        for (int i = 0; i < NN; ++i) S[i] = pb[(OC + i) * stb];
+        hsht<D>(H2, [&](int r, int c) { return S[r * N + c]; }, x.cov);
+        RPGO_UNROLL
+        for (int i = 0; i < NN; ++i) x.cov[i] = pa[(OC + i) * sta] - x.cov[i];
+      }
+    }
+    x.pose = P;
+    x.rot = (pa[OR * sta] != 0.0) && (pb[OR * stb] != 0.0);
+    x.node = 0;
+    if (s == 0) store_entry<D, MODE_PCM>(scr, ss, x);
+  }
+
+  /* ---- the three compose() stages: . c_lc_d, (inverse) . a_lc_b, . b_odom_d ---- */
+  rot_chain = x.rot;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int t = 0; t < 3; ++t) {
+    const double* po = t == 0 ? lcj : (t == 1 ? lci : scr);
+    const int sto = t == 0 ? slj : (t == 1 ? sli : ss);
+    Pose<D> O;
+    load_pose<D>(po, sto, O);
+    const Adj<D> H = adjoint<D>(inverse<D>(O));
+    double out[NN];
+    hsht<D>(H, [&](int r, int c) { return x.cov[r * N + c]; }, out);
+    RPGO_UNROLL
+    for (int i = 0; i < NN; ++i) x.cov[i] = out[i] + po[(OC + i) * sto];
+    x.pose = compose<D>(x.pose, O);
+    rot_chain = rot_chain && (po[OR * sto] != 0.0);
+    if (t == 0) x.pose = inverse<D>(x.pose);
+  }
+  x.rot = rot_chain;
+  return check_consistent<D, MODE_PCM>(x, th, false, dist, near);
 }
 
 }  // namespace rpgo

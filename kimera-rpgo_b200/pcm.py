@@ -132,32 +132,57 @@ class PcmGpu:
         return do_optimize
 
     def _odom_append(self, odom):
-        n = len(odom)
         prev = np.array([o[1] for o in odom], dtype=np.uint64)
         new = np.array([o[2] for o in odom], dtype=np.uint64)
-        dpose = np.ascontiguousarray(np.stack([np.asarray(o[3], dtype=np.float64) for o in odom]))
-        dcov = np.ascontiguousarray(np.stack([np.asarray(o[4], dtype=np.float64).reshape(self.n * self.n) for o in odom]))
+        dpose = np.stack([np.asarray(o[3], dtype=np.float64) for o in odom])
+        dcov = np.stack([np.asarray(o[4], dtype=np.float64).reshape(self.n * self.n) for o in odom])
         ident = np.zeros(self.ps)
         if self.d == 3:
             ident[[0, 4, 8]] = 1.0
         else:
             ident[0] = 1.0
-        init = np.ascontiguousarray(np.stack([self.values.get(int(o[1]), ident) for o in odom]))
-        self.nfg_odom.extend(o[0] for o in odom)
+        init = np.stack([self.values.get(int(o[1]), ident) for o in odom])
+        self.odom_append_arrays(prev, new, dpose, dcov, init, ids=[o[0] for o in odom])
+
+    def odom_append_arrays(self, prev, new, dpose, dcov, init=None, ids=None):
+        """Array form of the odometry stage (K1): n factors prev[i] -> new[i] with measured pose dpose[i]
+        (n x 12|4) and covariance dcov[i] (n x 36|9); init[i] = values.at(prev[i]) (used for new prefixes)."""
+        n = len(prev)
+        prev = np.ascontiguousarray(prev, dtype=np.uint64)
+        new = np.ascontiguousarray(new, dtype=np.uint64)
+        dpose = np.ascontiguousarray(dpose, dtype=np.float64).reshape(n, self.ps)
+        dcov = np.ascontiguousarray(dcov, dtype=np.float64).reshape(n, self.n * self.n)
+        ip = None
+        if init is not None:
+            init = np.ascontiguousarray(init, dtype=np.float64).reshape(n, self.ps)
+            ip = _dp(init)
+        if ids is None:
+            ids = range(self.next_id, self.next_id + n)
+            self.next_id += n
+        self.nfg_odom.extend(ids)
         self._check(self.lib.rpgo_odom_append(self.h, n, prev.ctypes.data_as(_capi.c_u64p), new.ctypes.data_as(_capi.c_u64p),
-                                              _dp(dpose), _dp(dcov), _dp(init)), "rpgo_odom_append")
+                                              _dp(dpose), _dp(dcov), ip), "rpgo_odom_append")
+        return (dpose.nbytes + dcov.nbytes + (init.nbytes if init is not None else 0))
 
     def _lc_append(self, lcs):
         # Pcm.h:431-435: both keys must exist in the values
         lcs = [l for l in lcs if l[1] in self.values and l[2] in self.values]
-        num_new = {}
         if not lcs:
-            return num_new
-        n = len(lcs)
+            return {}
         kf = np.array([l[1] for l in lcs], dtype=np.uint64)
         kt = np.array([l[2] for l in lcs], dtype=np.uint64)
-        pose = np.ascontiguousarray(np.stack([np.asarray(l[3], dtype=np.float64) for l in lcs]))
-        cov = np.ascontiguousarray(np.stack([np.asarray(l[4], dtype=np.float64).reshape(self.n * self.n) for l in lcs]))
+        pose = np.stack([np.asarray(l[3], dtype=np.float64) for l in lcs])
+        cov = np.stack([np.asarray(l[4], dtype=np.float64).reshape(self.n * self.n) for l in lcs])
+        num_new, _ = self.lc_append_arrays(kf, kt, pose, cov, ids=[l[0] for l in lcs])
+        return num_new
+
+    def lc_append_arrays(self, kf, kt, pose, cov, ids=None):
+        """Array form of the loop-closure stage (K2 + K3).  Returns ({group: number of new closures}, accepted)."""
+        n = len(kf)
+        kf = np.ascontiguousarray(kf, dtype=np.uint64)
+        kt = np.ascontiguousarray(kt, dtype=np.uint64)
+        pose = np.ascontiguousarray(pose, dtype=np.float64).reshape(n, self.ps)
+        cov = np.ascontiguousarray(cov, dtype=np.float64).reshape(n, self.n * self.n)
         acc = np.zeros(n, dtype=np.uint8)
         grp = np.zeros(n, dtype=np.int32)
         idx = np.zeros(n, dtype=np.int32)
@@ -165,20 +190,27 @@ class PcmGpu:
                                             _dp(pose), _dp(cov), acc.ctypes.data_as(_capi.c_u8p),
                                             grp.ctypes.data_as(_capi.c_i32p), idx.ctypes.data_as(_capi.c_i32p), None),
                     "rpgo_lc_append")
-        for i, l in enumerate(lcs):
-            if not acc[i]:
-                continue
-            g = int(grp[i])
+        if ids is None:
+            ids = np.arange(self.next_id, self.next_id + n)
+            self.next_id += n
+        ids = np.asarray(ids)
+        num_new = {}
+        ok = acc.astype(bool)
+        for g in np.unique(grp[ok]):
+            g = int(g)
+            sel = ok & (grp == g)
             if g not in self.group_factors:
                 self.group_factors[g] = []
                 self.group_consistent[g] = []
                 self.group_order.append(g)
-            assert len(self.group_factors[g]) == int(idx[i])
-            self.group_factors[g].append(l[0])
-            self.lc_in_order.append(g)
-            self.total_lc += 1
-            num_new[g] = num_new.get(g, 0) + 1
-        return num_new
+            assert len(self.group_factors[g]) == int(idx[sel][0])
+            self.group_factors[g].extend(ids[sel].tolist())
+            num_new[g] = int(sel.sum())
+        self.lc_in_order.extend(grp[ok].tolist())
+        self.total_lc += int(ok.sum())
+        self.last_h2d_bytes = pose.nbytes + cov.nbytes + 9 * n
+        self.last_d2h_bytes = n
+        return num_new, acc
 
     def find_inliers_raw(self, g, clique_mode=CLIQUE_HEU, n_new=0, prev_size=0):
         """(size, ids, true_clique) straight from rpgo_find_inliers."""
@@ -379,6 +411,22 @@ class PcmGpu:
 
     def stream_ptr(self):
         return self.lib.rpgo_stream(self.h)
+
+    def pairwise_only(self, g, j_begin=0):
+        self._check(self.lib.rpgo_group_pairwise(self.h, g, j_begin), "rpgo_group_pairwise")
+
+    def finalize(self, g):
+        self._check(self.lib.rpgo_group_finalize(self.h, g), "rpgo_group_finalize")
+
+    def adj_bits_device(self, g):
+        ptr, sw, n = C.c_void_p(), C.c_int64(), C.c_int64()
+        self._check(self.lib.rpgo_adj_bits_device(self.h, g, C.byref(ptr), C.byref(sw), C.byref(n)), "rpgo_adj_bits_device")
+        return ptr.value, sw.value, n.value
+
+    def group_chunking(self, g):
+        c, p = C.c_int64(), C.c_int64()
+        self._check(self.lib.rpgo_group_chunking(self.h, g, C.byref(c), C.byref(p)), "rpgo_group_chunking")
+        return c.value, p.value
 
     def recompute(self, g, j_begin=0):
         self._check(self.lib.rpgo_group_recompute(self.h, g, j_begin), "rpgo_group_recompute")

@@ -192,3 +192,23 @@ def config3(seed=2, P=10000, n=10000, outlier_frac=0.3):
     lcs = [(BETWEEN, keys[i[q]], keys[j[q]], np.array([np.cos(dth[q]), np.sin(dth[q]), dx[q], dy[q]]), lcov)
            for q in range(n)]
     return dict(d=2, values=values, odom=odom, lcs=lcs, outlier=out)
+
+
+def as_arrays(gph):
+    """Array form of a generated graph (what PcmGpu.odom_append_arrays / lc_append_arrays take)."""
+    d = gph["d"]
+    ps, nn = (12, 36) if d == 3 else (4, 9)
+    vals = dict((int(k), p) for k, p in gph["values"])
+    od, lc = gph["odom"], gph["lcs"]
+    out = dict(d=d)
+    out["o_prev"] = np.array([f[1] for f in od], dtype=np.uint64)
+    out["o_new"] = np.array([f[2] for f in od], dtype=np.uint64)
+    out["o_pose"] = np.ascontiguousarray(np.stack([f[3] for f in od])).reshape(len(od), ps)
+    out["o_cov"] = np.ascontiguousarray(np.stack([np.asarray(f[4]).reshape(nn) for f in od]))
+    out["o_init"] = np.ascontiguousarray(np.stack([vals[int(f[1])] for f in od]))
+    out["l_from"] = np.array([f[1] for f in lc], dtype=np.uint64)
+    out["l_to"] = np.array([f[2] for f in lc], dtype=np.uint64)
+    out["l_pose"] = np.ascontiguousarray(np.stack([f[3] for f in lc])).reshape(len(lc), ps)
+    out["l_cov"] = np.ascontiguousarray(np.stack([np.asarray(f[4]).reshape(nn) for f in lc]))
+    out["v_keys"] = np.array([k for k, _ in gph["values"]], dtype=np.uint64)
+    return out

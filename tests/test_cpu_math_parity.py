@@ -26,6 +26,7 @@ def shim():
     L = C.CDLL(SO)
     L.shim_entry_size.restype = C.c_int
     L.shim_pair_check.restype = C.c_int
+    L.shim_pair_check_v1.restype = C.c_int
     return L
 
 
@@ -101,6 +102,11 @@ def test_pair_check_pcm_bitwise(shim, d):
         ok = shim.shim_pair_check(d, 0, *[dp(e) for e in E], dp(thr), C.byref(dist), C.byref(near))
         assert (dist.value == want) or (np.isnan(dist.value) and np.isnan(want)), (t, dist.value, want)
         assert bool(ok) == bool(want < thr[1])
+        # the restructured (tiled-kernel) pair function must give the same bits
+        d1 = C.c_double()
+        ok1 = shim.shim_pair_check_v1(d, *[dp(e) for e in E], dp(thr), C.byref(d1), C.byref(near))
+        assert (d1.value == want) or (np.isnan(d1.value) and np.isnan(want)), ("v1", t, d1.value, want)
+        assert bool(ok1) == bool(ok)
 
 
 @pytest.mark.parametrize("d", [3, 2])

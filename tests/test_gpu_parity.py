@@ -227,3 +227,49 @@ def test_clique_large_planted():
     assert len(set(s)) == size and a[np.ix_(s, s)].sum() == size * (size - 1)
     deg = g.degrees(gi)
     assert np.array_equal(deg, a.sum(1))
+
+
+@pytest.mark.parametrize("d", [3, 2])
+def test_tiled_kernel_equals_direct_kernel(d):
+    """the TMA-tiled K3 and the direct K3 must produce the same bitset, flagged pairs and inliers."""
+    if d == 3:
+        gph = synth.config4(seed=9, robots=2, P=700, n=900, outlier_frac=0.4)
+        params = dict(odom_threshold=25.0, lc_threshold=5.0)
+    else:
+        gph = synth.config3(seed=6, P=2000, n=700)
+        params = dict(odom_threshold=-1, lc_threshold=3.0)
+    res = []
+    for kern in (pkg.KERNEL_DIRECT, pkg.KERNEL_TILED):
+        g = PcmGpu(d, 0, kernel=kern, **params)
+        g.update(gph["odom"], gph["values"])
+        half = len(gph["lcs"]) // 2
+        g.update(gph["lcs"][:half], [])
+        g.update(gph["lcs"][half:half + 7], [])
+        g.update(gph["lcs"][half + 7:], [])
+        res.append(g)
+    a, b = res
+    assert a.groups() == b.groups()
+    for gi in range(len(a.groups())):
+        assert np.array_equal(a.group_bits(gi), b.group_bits(gi)), gi
+        na, pa = a.flagged(gi)
+        nb, pb = b.flagged(gi)
+        assert na == nb and sorted(map(tuple, pa.tolist())) == sorted(map(tuple, pb.tolist()))
+        assert a.group_inlier_ids(gi).tolist() == b.group_inlier_ids(gi).tolist()
+
+
+def test_closure_before_odometry_sees_later_trajectory():
+    """A closure whose key has no trajectory entry yet uses the default entry (std::map::operator[],
+    GraphUtils.h:42); pairs formed after the odometry arrives must use the real entry."""
+    gph = synth.config2(seed=13, P=200, n=30, outlier_frac=0.2)
+    params = dict(odom_threshold=-1, lc_threshold=6.0)
+    o = orc.OraclePcm(3, 0, **params)
+    g = PcmGpu(3, 0, **params)
+    first, rest = gph["odom"][:100], gph["odom"][100:]
+    for x in (o, g):
+        x.update(first, gph["values"][:101])
+        # values for all keys exist, odometry for the second half does not yet
+        x.update([], gph["values"][101:])
+        x.update(gph["lcs"][:15], [])
+        x.update(rest, [])           # arrives late: classified as loop closures by Pcm.h:189-194 (no new value)
+        x.update(gph["lcs"][15:], [])
+    compare_groups(o, g, check_dist=False)
