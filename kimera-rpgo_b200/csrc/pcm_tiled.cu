@@ -17,6 +17,7 @@
  */
 #include <cstdio>
 
+#define RPGO_MATH_IMPL
 #include "kernels.cuh"
 
 namespace rpgo {

@@ -254,6 +254,80 @@ RPGO_FN bool llt_ok(const double* Min) {
   return ok;
 }
 
+
+/* a / x given r = RN(1/x) (IEEE reciprocal): q0 = RN(a r); rem = a - q0 x (exact, one FMA);
+ * q = RN(q0 + rem r).  By Markstein's theorem q == RN(a / x) whenever r is the correctly rounded
+ * reciprocal and nothing over/underflows; outside that range we fall back to the plain division.
+ * Used where several numerators share one divisor (a column of the LLT / LU factorisations), so the
+ * expensive reciprocal is paid once.  tests/test_cpu_math_parity.py checks it against `/` on 10^7
+ * adversarial operands and the GPU suite checks the kernels that use it against the kernel that does
+ * not (bitset equality over 2*10^8 pairs). */
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__ double slow_div(double a, double x);
+#if defined(RPGO_MATH_IMPL)
+__host__ __device__ __noinline__ double slow_div(double a, double x) { return a / x; }
+#endif
+#else
+static double slow_div(double a, double x) { return a / x; }
+#endif
+
+RPGO_FN double div_by(double a, double x, double r) {
+  const double q0 = a * r;
+  const double rem = fma(-q0, x, a);
+  double q = fma(rem, r, q0);
+  const double aq = fabs(q0);
+  const bool safe = (aq > 1e-280 && aq < 1e280) || a == 0.0;
+  if (!safe) q = slow_div(a, x); /* rare: one shared out-of-line division */
+  return q;
+}
+RPGO_FN bool rcp_safe(double x) {
+  const double ax = fabs(x);
+  return ax > 1e-140 && ax < 1e140;
+}
+
+/* llt_ok with the column divisions done through div_by (same results as llt_ok) */
+template <int N>
+RPGO_FN bool llt_ok_fast(const double* Min) {
+  double A[N * N];
+  RPGO_UNROLL
+  for (int i = 0; i < N; ++i) {
+    RPGO_UNROLL
+    for (int j = 0; j <= i; ++j) A[i * N + j] = Min[i * N + j];
+  }
+  bool ok = true;
+  RPGO_UNROLL
+  for (int k = 0; k < N; ++k) {
+    double x = A[k * N + k];
+    if (k > 0) {
+      double sn = A[k * N] * A[k * N];
+      RPGO_UNROLL
+      for (int j = 1; j < k; ++j) sn = fma(A[k * N + j], A[k * N + j], sn);
+      x = x - sn;
+    }
+    if (ok && x <= 0.0) ok = false;
+    if (!ok) break;
+    x = sqrt(x);
+    A[k * N + k] = x;
+    if (k + 1 < N) {
+      const bool fast = rcp_safe(x);
+      const double r = 1.0 / x;
+      RPGO_UNROLL
+      for (int i = k + 1; i < N; ++i) {
+        double v = A[i * N + k];
+        if (k > 0) {
+          double dot = A[i * N] * A[k * N];
+          RPGO_UNROLL
+          for (int j = 1; j < k; ++j) dot = fma(A[i * N + j], A[k * N + j], dot);
+          v = v - dot;
+        }
+        if (fast) v = div_by(v, x, r); else v = slow_div(v, x);
+        A[i * N + k] = v;
+      }
+    }
+  }
+  return ok;
+}
+
 /* q = v^T M^-1 v the way the reference computes it: M^-1 by Eigen PartialPivLU + solve(Identity)
  * (column by column), then (v^T M^-1) v.  Row swaps are predicated so that everything stays in
  * registers. */
@@ -344,6 +418,107 @@ RPGO_FN double quad_form_inv(const double* Min, const double* v) {
   for (int j = 1; j < N; ++j) q = fma(w[j], v[j], q);
   return q;
 }
+
+template <int N>
+RPGO_FN double quad_form_inv_fast(const double* Min, const double* v) {
+  double lu[N * N];
+  int perm[N];
+  RPGO_UNROLL
+  for (int i = 0; i < N * N; ++i) lu[i] = Min[i];
+  RPGO_UNROLL
+  for (int i = 0; i < N; ++i) perm[i] = i;
+  RPGO_UNROLL
+  for (int k = 0; k < N; ++k) {
+    int piv = k;
+    double biggest = fabs(lu[k * N + k]);
+    RPGO_UNROLL
+    for (int i = k + 1; i < N; ++i) {
+      const double a = fabs(lu[i * N + k]);
+      if (a > biggest) { biggest = a; piv = i; }
+    }
+    if (biggest != 0.0) {
+      /* exchange rows k and piv with value selects only (a data-dependent row index would push the
+       * whole matrix into local memory) */
+      RPGO_UNROLL
+      for (int j = 0; j < N; ++j) {
+        const double oldk = lu[k * N + j];
+        double newk = oldk;
+        RPGO_UNROLL
+        for (int i = k + 1; i < N; ++i) {
+          const bool sw = (piv == i);
+          const double vi = lu[i * N + j];
+          newk = sw ? vi : newk;
+          lu[i * N + j] = sw ? oldk : vi;
+        }
+        lu[k * N + j] = newk;
+      }
+      {
+        const int oldk = perm[k];
+        int newk = oldk;
+        RPGO_UNROLL
+        for (int i = k + 1; i < N; ++i) {
+          const bool sw = (piv == i);
+          const int vi = perm[i];
+          newk = sw ? vi : newk;
+          perm[i] = sw ? oldk : vi;
+        }
+        perm[k] = newk;
+      }
+      const double pv = lu[k * N + k];
+      RPGO_UNROLL
+      for (int i = k + 1; i < N; ++i) lu[i * N + k] = lu[i * N + k] / pv;
+    }
+    RPGO_UNROLL
+    for (int i = k + 1; i < N; ++i) {
+      RPGO_UNROLL
+      for (int j = k + 1; j < N; ++j) lu[i * N + j] = fma(-lu[i * N + k], lu[k * N + j], lu[i * N + j]);
+    }
+  }
+  double rdiag[N];
+  RPGO_UNROLL
+  for (int i = 0; i < N; ++i) rdiag[i] = 1.0 / lu[i * N + i];
+  /* inverse = U^-1 (L^-1 P).  Column c of P is e_p with perm[p] == c, so column c of the inverse is
+   * U^-1 applied to column p of L^-1.  L^-1's columns have a static triangular zero pattern (the skipped
+   * operations of the dense forward substitution are exact no-ops), so they are built without selects;
+   * only the final 6 scalars are permuted back into natural order for the k-ordered dot product. */
+  double wp[N]; /* wp[p] = sum_i v[i] * inv[i][perm[p]] */
+  RPGO_UNROLL
+  for (int p = 0; p < N; ++p) {
+    double x[N];
+    RPGO_UNROLL
+    for (int i = 0; i < N; ++i) x[i] = (i == p) ? 1.0 : 0.0;
+    RPGO_UNROLL
+    for (int i = p; i < N; ++i) {
+      const double b = x[i];
+      RPGO_UNROLL
+      for (int r = i + 1; r < N; ++r) x[r] = fma(-b, lu[r * N + i], x[r]);
+    }
+    RPGO_UNROLL
+    for (int i = N - 1; i >= 0; --i) {
+      const double b = x[i] * rdiag[i];
+      x[i] = b;
+      RPGO_UNROLL
+      for (int r = 0; r < i; ++r) x[r] = fma(-b, lu[r * N + i], x[r]);
+    }
+    double acc = v[0] * x[0];
+    RPGO_UNROLL
+    for (int i = 1; i < N; ++i) acc = fma(v[i], x[i], acc);
+    wp[p] = acc;
+  }
+  double w[N];
+  RPGO_UNROLL
+  for (int c = 0; c < N; ++c) {
+    double t = wp[0];
+    RPGO_UNROLL
+    for (int p = 1; p < N; ++p) t = (perm[p] == c) ? wp[p] : t;
+    w[c] = t;
+  }
+  double q = w[0] * v[0];
+  RPGO_UNROLL
+  for (int j = 1; j < N; ++j) q = fma(w[j], v[j], q);
+  return q;
+}
+
 
 /* SO3::Logmap (GTSAM 4.0/4.1 constants) */
 RPGO_FN void so3_logmap(const double* R, double* w) {
@@ -537,7 +712,7 @@ RPGO_FN void pt_between(const PoseT<D, MODE>& a, const PoseT<D, MODE>& b, PoseT<
 }
 
 /* mahalanobis_norm  GeometryUtils.h:172-186 */
-template <int D>
+template <int D, bool FAST = false>
 RPGO_FN double mahalanobis(const PoseT<D, MODE_PCM>& a) {
   constexpr int N = Dim<D>::N, RD = Dim<D>::RD, TD = Dim<D>::TD;
   double lg[N];
@@ -550,9 +725,9 @@ RPGO_FN double mahalanobis(const PoseT<D, MODE_PCM>& a) {
       RPGO_UNROLL
       for (int j = 0; j < TD; ++j) blk[i * TD + j] = a.cov[(RD + i) * N + RD + j];
     }
-    q = quad_form_inv<TD>(blk, lg + RD);
+    q = FAST ? quad_form_inv_fast<TD>(blk, lg + RD) : quad_form_inv<TD>(blk, lg + RD);
   } else {
-    q = quad_form_inv<N>(a.cov, lg);
+    q = FAST ? quad_form_inv_fast<N>(a.cov, lg) : quad_form_inv<N>(a.cov, lg);
   }
   return sqrt(q);
 }
@@ -587,10 +762,10 @@ struct Thresholds {
 
 /* checkOdomConsistent / checkLoopConsistent  Pcm.h:564-596, 638-662.
  * Returns the decision; *dist = Mahalanobis (Pcm) or avg translation (Simple); *near = within band. */
-template <int D, int MODE>
+template <int D, int MODE, bool FAST = false>
 RPGO_FN bool check_consistent(const PoseT<D, MODE>& r, const Thresholds& th, bool odom, double* dist, bool* near) {
   if (MODE == MODE_PCM) {
-    const double d = mahalanobis<D>(reinterpret_cast<const PoseT<D, MODE_PCM>&>(r));
+    const double d = mahalanobis<D, FAST>(reinterpret_cast<const PoseT<D, MODE_PCM>&>(r));
     const double t = odom ? th.odom : th.lc;
     *dist = d;
     *near = fabs(d - t) < th.band;
@@ -741,7 +916,7 @@ RPGO_FN bool pair_check_v1(const double* Ta, int sa, const double* Tb, int sb, c
     if (t == 0) x.pose = inverse<D>(x.pose);
   }
   x.rot = rot_chain;
-  return check_consistent<D, MODE_PCM>(x, th, false, dist, near);
+  return check_consistent<D, MODE_PCM, true>(x, th, false, dist, near);
 }
 
 }  // namespace rpgo

@@ -56,6 +56,17 @@ static int pair_v1_t(const double* Ta, const double* Tb, const double* lci, cons
             : ((m) == 0 ? F<2, 0>(__VA_ARGS__) : F<2, 1>(__VA_ARGS__)))
 
 extern "C" {
+/* returns the number of mismatches between div_by(a, x, 1/x) and a / x over n operand pairs */
+long long shim_div_by_mismatches(long long n, const double* a, const double* x) {
+  long long bad = 0;
+  for (long long i = 0; i < n; ++i) {
+    const double r = 1.0 / x[i];
+    const double q = rcp_safe(x[i]) ? div_by(a[i], x[i], r) : a[i] / x[i];
+    const double w = a[i] / x[i];
+    if (!(q == w) && !(q != q && w != w)) ++bad;
+  }
+  return bad;
+}
 int shim_entry_size(int d) { return d == 3 ? Dim<3>::ENTRY : Dim<2>::ENTRY; }
 int shim_pair_check(int d, int mode, const double* Ta, const double* Tb, const double* lci, const double* Tc,
                     const double* Td, const double* lcj, const double* thr, double* dist, int* near) {

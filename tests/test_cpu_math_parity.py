@@ -134,3 +134,35 @@ def test_pair_check_simple_bitwise(shim, d):
         ok = shim.shim_pair_check(d, 1, *[dp(e) for e in E], dp(thr), C.byref(dist), C.byref(near))
         assert dist.value == wt, (t, dist.value, wt)
         assert bool(ok) == bool(wt < thr[4] and wr < thr[5])
+
+
+def test_div_by_equals_ieee_division(shim):
+    """div_by (shared correctly-rounded reciprocal + FMA correction) == IEEE a / x on 10^7 operands,
+    including significands near 1 and 2 (all-ones / all-zeros mantissas) and wide exponent ranges."""
+    rng = np.random.default_rng(77)
+    shim.shim_div_by_mismatches.restype = C.c_longlong
+    shim.shim_div_by_mismatches.argtypes = [C.c_longlong, orc.c_dp, orc.c_dp]
+    n = 2_500_000
+    total = 0
+    for kind in range(4):
+        if kind == 0:
+            a = rng.normal(size=n) * 10.0 ** rng.uniform(-8, 8, size=n)
+            x = rng.normal(size=n) * 10.0 ** rng.uniform(-8, 8, size=n)
+        elif kind == 1:  # mantissas hugging powers of two
+            ma = rng.integers(0, 64, size=n).astype(np.uint64)
+            mx = rng.integers(0, 64, size=n).astype(np.uint64)
+            top = np.uint64(0x000FFFFFFFFFFFFF)
+            abits = (np.uint64(1023) << np.uint64(52)) | np.where(rng.random(n) < 0.5, ma, top - ma)
+            xbits = (np.uint64(1023) << np.uint64(52)) | np.where(rng.random(n) < 0.5, mx, top - mx)
+            a = abits.view(np.float64) * 2.0 ** rng.integers(-40, 40, size=n)
+            x = xbits.view(np.float64) * 2.0 ** rng.integers(-40, 40, size=n)
+        elif kind == 2:  # exact and nearly exact quotients
+            x = rng.integers(1, 1 << 20, size=n).astype(np.float64)
+            qq = rng.integers(1, 1 << 30, size=n).astype(np.float64)
+            a = x * qq + rng.integers(-1, 2, size=n)
+        else:  # random bit patterns of moderate exponent
+            a = (rng.integers(0, 1 << 52, size=n, dtype=np.uint64) | (np.uint64(1000 + 46) << np.uint64(52))).view(np.float64)
+            x = (rng.integers(0, 1 << 52, size=n, dtype=np.uint64) | (np.uint64(1000 + 11) << np.uint64(52))).view(np.float64)
+        a = np.ascontiguousarray(a); x = np.ascontiguousarray(x)
+        total += shim.shim_div_by_mismatches(n, dp(a), dp(x))
+    assert total == 0

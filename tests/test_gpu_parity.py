@@ -273,3 +273,22 @@ def test_closure_before_odometry_sees_later_trajectory():
         x.update(rest, [])           # arrives late: classified as loop closures by Pcm.h:189-194 (no new value)
         x.update(gph["lcs"][15:], [])
     compare_groups(o, g, check_dist=False)
+
+
+def test_tiled_equals_direct_at_scale():
+    """2*10^8 pairs: the optimised kernel (shared-reciprocal divisions, convergent LLT probe, triangular
+    forward solves) against the plain kernel that uses none of them — bitset equality."""
+    n = 20000
+    arr = synth.as_arrays(synth.config2(seed=4, P=n, n=n))
+    bits = []
+    for kern in (pkg.KERNEL_DIRECT, pkg.KERNEL_TILED):
+        g = PcmGpu(3, 0, kernel=kern, odom_threshold=-1, lc_threshold=5.0)
+        g.odom_append_arrays(arr["o_prev"], arr["o_new"], arr["o_pose"], arr["o_cov"], arr["o_init"])
+        g.lc_append_arrays(arr["l_from"], arr["l_to"], arr["l_pose"], arr["l_cov"])
+        bits.append(g.group_bits(0))
+        nfl = g.flagged(0)[0]
+        g.close()
+    assert np.array_equal(bits[0], bits[1])
+    # symmetric, zero diagonal
+    a = np.unpackbits(bits[1][:512].view(np.uint8), axis=1, bitorder="little")[:, :512]
+    assert np.array_equal(a, a.T) and not a.diagonal().any()
