@@ -187,11 +187,7 @@ def main():
     # ---- resident state for the kernel-timed leg -------------------------------------------------
     g = pkg.PcmGpu(3, 0, device=local, kernel=a.kernel, rank=rank, world=world, **params)
     g.odom_append_arrays(arr["o_prev"], arr["o_new"], arr["o_pose"], arr["o_cov"], arr["o_init"])
-    for k in arr["v_keys"]:
-        pass
-    g.lc_append_arrays(arr["l_from"], arr["l_to"], arr["l_pose"], arr["l_cov"])
-    if world > 1:
-        par.allgather_adjacency(g, 0, device)
+    g.lc_append_arrays(arr["l_from"], arr["l_to"], arr["l_pose"], arr["l_cov"])  # all-gathers when world > 1
     st = torch.cuda.ExternalStream(g.stream_ptr(), device=device)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
 
@@ -264,10 +260,8 @@ def main():
             t0 = time.perf_counter()
             p = pkg.PcmGpu(3, 0, device=local, kernel=a.kernel, rank=rank, world=world, **params)
             h2d = p.odom_append_arrays(arr["o_prev"], arr["o_new"], arr["o_pose"], arr["o_cov"], arr["o_init"])
-            p.lc_append_arrays(arr["l_from"], arr["l_to"], arr["l_pose"], arr["l_cov"])
+            p.lc_append_arrays(arr["l_from"], arr["l_to"], arr["l_pose"], arr["l_cov"])  # incl. all-gather when world > 1
             h2d += p.last_h2d_bytes
-            if world > 1:
-                par.allgather_adjacency(p, 0, device)
             sz, ids, _ = p.find_inliers_raw(0, pkg.CLIQUE_HEU)
             d2h = p.last_d2h_bytes + 4 * int(sz) + 8
             p.sync()

@@ -744,7 +744,7 @@ int rpgo_find_inliers(rpgo_handle* h, int32_t gi, int32_t clique_mode, int64_t n
   if (n <= 0 || !h->loop_check) { h->err = "find_inliers: empty group or loop check disabled"; return RPGO_ERR_INVALID; }
   cudaStream_t st = h->stream;
   const int W = (n + 31) / 32;
-  const int64_t blocks = 296;
+  const int64_t blocks = 148 * 8;
   H_CHECK_CUDA(h, h->c_degmask.ensure((size_t)W * 4 + 64, 0, st));
   H_CHECK_CUDA(h, h->c_picks.ensure((size_t)n * 4 + 64, 0, st));
   H_CHECK_CUDA(h, h->c_elim.ensure((size_t)n * 4 + 64, 0, st));

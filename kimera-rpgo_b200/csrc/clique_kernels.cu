@@ -29,7 +29,7 @@
 
 namespace rpgo {
 
-static constexpr int HEU_THREADS = 256;
+static constexpr int HEU_THREADS = 128;
 
 __global__ void degmask_kernel(const int32_t* __restrict__ deg, int n, int M, uint32_t* mask, int words) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -320,12 +320,4 @@ int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_
   return M;
 }
 
-}  // namespace rpgo
-
-namespace rpgo {
-/* K5 placeholder until the exact branch-and-bound lands (see clique_exact.cu) */
-__attribute__((weak)) int clique_exact(const uint32_t*, int64_t, int, const int32_t*, CliqueScratch, int32_t*, int64_t*,
-                                       cudaStream_t) {
-  return -3;
-}
 }  // namespace rpgo

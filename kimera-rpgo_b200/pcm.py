@@ -55,6 +55,7 @@ class PcmGpu:
         if rc != 0:
             raise RpgoError("rpgo_create failed with status %d (no usable CUDA device? there is no CPU fallback)" % rc)
         self.d, self.mode = d, mode
+        self.auto_exchange = True
         self.ps = 12 if d == 3 else 4
         self.n = 6 if d == 3 else 3
         self.incremental = bool(incremental)
@@ -210,6 +211,13 @@ class PcmGpu:
         self.total_lc += int(ok.sum())
         self.last_h2d_bytes = pose.nbytes + cov.nbytes + 9 * n
         self.last_d2h_bytes = n
+        if self.cfg.world > 1 and self.loop_check and self.auto_exchange:
+            # multi-GPU: this rank computed only its row chunks; all-gather them and rebuild the mirror
+            from . import parallel
+            import torch
+            dev = torch.device("cuda", torch.cuda.current_device())
+            for g in num_new:
+                parallel.allgather_adjacency(self, g, dev)
         return num_new, acc
 
     def find_inliers_raw(self, g, clique_mode=CLIQUE_HEU, n_new=0, prev_size=0):

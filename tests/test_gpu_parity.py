@@ -292,3 +292,30 @@ def test_tiled_equals_direct_at_scale():
     # symmetric, zero diagonal
     a = np.unpackbits(bits[1][:512].view(np.uint8), axis=1, bitorder="little")[:, :512]
     assert np.array_equal(a, a.T) and not a.diagonal().any()
+
+
+def test_clique_exact_matches_reference_fmc():
+    """K5 against the reference's own FMC::maxClique (size AND ids, i.e. the same tie-break)."""
+    rng = np.random.default_rng(24)
+    g = PcmGpu(3, 0)
+    ref = orc.ref_clique_exact if orc.ref_fmc() is not None else orc.clique_exact
+    for t in range(50):
+        n = int(rng.integers(1, 90))
+        a = rand_graph(rng, n, rng.uniform(0.05, 0.9))
+        gi = g.load_adjacency(a)
+        k, ids, _ = g.find_inliers_raw(gi, pkg.CLIQUE_EXACT)
+        kr, ir = ref(a)
+        assert k == kr and ids.tolist() == ir.tolist(), (t, n, ids.tolist(), ir.tolist())
+
+
+def test_clique_exact_planted():
+    rng = np.random.default_rng(25)
+    n, k = 1500, 40
+    a = rand_graph(rng, n, 0.1)
+    members = np.sort(rng.choice(n, size=k, replace=False))
+    a[np.ix_(members, members)] = 1
+    np.fill_diagonal(a, 0)
+    g = PcmGpu(3, 0)
+    gi = g.load_adjacency(a)
+    size, ids, _ = g.find_inliers_raw(gi, pkg.CLIQUE_EXACT)
+    assert size == k and ids.tolist() == members.tolist()
