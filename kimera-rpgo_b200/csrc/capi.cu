@@ -91,6 +91,11 @@ struct Group {
 
 constexpr int64_t FLAG_CAP = 1 << 20;
 
+PinBuf& pinned_staging() {
+  static thread_local PinBuf buf;
+  return buf;
+}
+
 }  // namespace
 
 struct rpgo_handle {
@@ -113,8 +118,7 @@ struct rpgo_handle {
   std::vector<Group*> groups;
   std::map<std::pair<uint8_t, uint8_t>, int32_t> gindex;
 
-  /* staging */
-  PinBuf pin;
+  /* staging (the pinned host buffer is per thread, shared by successive handles: cudaMallocHost is slow) */
   DevBuf d_stage;
   DevBuf d_lcent, d_ok, d_dist;
   /* clique scratch */
@@ -229,8 +233,11 @@ static int run_pairwise(rpgo_handle* h, Group* g, int64_t j_begin, double* dist_
   int kernel = h->cfg.kernel;
   {
     extern int g_direct_minb_set(int);
+    extern int g_tiled_variant_set(int);
     g_direct_minb_set(kernel == 13 ? 3 : kernel == 14 ? 4 : 2);
     if (kernel == 13 || kernel == 14) kernel = RPGO_KERNEL_DIRECT;
+    g_tiled_variant_set(kernel >= 20 && kernel <= 23 ? kernel - 20 : 2);
+    if (kernel >= 20 && kernel <= 23) kernel = RPGO_KERNEL_TILED;
   }
   if (dist_dev) kernel = RPGO_KERNEL_DIRECT;
   if (kernel == RPGO_KERNEL_AUTO) kernel = (h->mode == MODE_PCM) ? RPGO_KERNEL_TILED : RPGO_KERNEL_DIRECT;
@@ -369,7 +376,10 @@ int rpgo_odom_append(rpgo_handle* h, int64_t n, const uint64_t* prev_key, const 
   std::vector<int32_t> chain_start;            /* start entry per chain */
   std::unordered_map<uint8_t, int> open_chain; /* prefix -> chain index whose tail can be extended */
   std::unordered_map<int, uint64_t> chain_tail_key;
-  std::set<int32_t> produced;                  /* entries written by this batch */
+  std::set<int32_t> overwritten;               /* pre-existing entries re-written by this batch (rare) */
+  std::set<int32_t> seed_idx;                  /* host-written seed entries: ready before any kernel runs */
+  const int64_t first_new_entry = h->traj_n;   /* entries >= this index are produced by this batch */
+  h->key2idx.reserve(h->key2idx.size() + (size_t)n + 16);
   std::vector<std::pair<int32_t, int64_t>> seeds; /* (entry, step k) */
   int64_t new_entries = h->traj_n;
   bool need_flush_order = false;
@@ -390,6 +400,7 @@ int rpgo_odom_append(rpgo_handle* h, int64_t n, const uint64_t* prev_key, const 
         h->traj_dirty = true;
       }
       seeds.push_back({idx, k});
+      seed_idx.insert(idx);
     }
     const int32_t src = traj_lookup(h, prev_key[k]);
     int32_t out;
@@ -407,13 +418,13 @@ int rpgo_odom_append(rpgo_handle* h, int64_t n, const uint64_t* prev_key, const 
       chains[oc->second].push_back({src, out, k});
       chain_tail_key[oc->second] = new_key[k];
     } else {
-      if (produced.count(src)) need_flush_order = true; /* starts from an entry another chain writes */
+      if ((src >= first_new_entry && !seed_idx.count(src)) || overwritten.count(src)) need_flush_order = true; /* starts from an entry another chain writes */
       chains.push_back({{src, out, k}});
       chain_start.push_back(src);
       open_chain[prefix] = (int)chains.size() - 1;
       chain_tail_key[(int)chains.size() - 1] = new_key[k];
     }
-    produced.insert(out);
+    if (out < first_new_entry) overwritten.insert(out);
   }
   int rc = ensure_traj(h, new_entries);
   if (rc != RPGO_OK) return rc;
@@ -439,7 +450,7 @@ int rpgo_odom_append(rpgo_handle* h, int64_t n, const uint64_t* prev_key, const 
   const size_t bytes_pose = (size_t)n * PS * 8, bytes_cov = (size_t)n * NN * 8;
   const size_t off_cov = bytes_pose, off_out = off_cov + bytes_cov, off_chain = off_out + (size_t)n * 4;
   const size_t total = off_chain + chains.size() * sizeof(FoldChain) + 64;
-  char* pin = (char*)h->pin.ensure(total);
+  char* pin = (char*)pinned_staging().ensure(total);
   if (!pin) { h->err = "pinned staging allocation failed"; return RPGO_ERR_NOMEM; }
   double* p_pose = (double*)pin;
   double* p_cov = (double*)(pin + off_cov);
@@ -564,7 +575,7 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
   const size_t o_cov = (size_t)n * PS * 8, o_if = o_cov + (size_t)n * NN * 8, o_ib = o_if + (size_t)n * 4,
                o_ck = o_ib + (size_t)n * 4, o_dst = (o_ck + (size_t)n + 15) & ~size_t(15),
                total = o_dst + (size_t)n * 8;
-  char* pin = (char*)h->pin.ensure(total + (size_t)n * 9 + 64);
+  char* pin = (char*)pinned_staging().ensure(total + (size_t)n * 9 + 64);
   if (!pin) { h->err = "pinned staging allocation failed"; return RPGO_ERR_NOMEM; }
   memcpy(pin, pose, (size_t)n * PS * 8);
   memcpy(pin + o_cov, cov, (size_t)n * NN * 8);

@@ -81,10 +81,9 @@ __device__ __forceinline__ bool row_owned_t(const Shard& sh, int i) {
   return c == sh.rank || c == 2 * (int64_t)sh.world - 1 - sh.rank;
 }
 
-constexpr int TILE_WARPS = 4;   /* rows per pipeline stage (one per warp) */
 constexpr int TILE_SEG = 512;   /* rows per work item */
 
-template <int D>
+template <int D, int TILE_WARPS>
 struct TiledSmem {
   static constexpr int RN = Rec<D>::N, E = Rec<D>::E;
   static constexpr size_t JT = (size_t)RN * 32 * 8;                 /* column slab */
@@ -93,16 +92,16 @@ struct TiledSmem {
   static constexpr size_t BYTES = JT + IT + SCR + 64;
 };
 
-template <int D>
-__global__ void __launch_bounds__(TILE_WARPS * 32, 2)
+template <int D, int TILE_WARPS, int MINB>
+__global__ void __launch_bounds__(TILE_WARPS * 32, MINB)
     pairwise_tiled_kernel(GroupView g, const double* __restrict__ aos, const double* __restrict__ soa, int j_begin,
                           int cb_begin, Shard sh, Thresholds th, Flagged fl) {
   constexpr int RN = Rec<D>::N, E = Rec<D>::E;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* Jt = reinterpret_cast<double*>(smem_raw);
-  double* It = reinterpret_cast<double*>(smem_raw + TiledSmem<D>::JT);
-  double* Scr = reinterpret_cast<double*>(smem_raw + TiledSmem<D>::JT + TiledSmem<D>::IT);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TiledSmem<D>::JT + TiledSmem<D>::IT + TiledSmem<D>::SCR);
+  double* It = reinterpret_cast<double*>(smem_raw + TiledSmem<D, TILE_WARPS>::JT);
+  double* Scr = reinterpret_cast<double*>(smem_raw + TiledSmem<D, TILE_WARPS>::JT + TiledSmem<D, TILE_WARPS>::IT);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TiledSmem<D, TILE_WARPS>::JT + TiledSmem<D, TILE_WARPS>::IT + TiledSmem<D, TILE_WARPS>::SCR);
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int cb = cb_begin + blockIdx.y;          /* column slab */
@@ -125,8 +124,8 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 2)
   }
   __syncthreads();
   if (tid == 0) {
-    mbar_expect_tx(&bars[0], (uint32_t)TiledSmem<D>::JT);
-    tma_load_1d(Jt, soa + (size_t)cb * RN * 32, (uint32_t)TiledSmem<D>::JT, &bars[0]);
+    mbar_expect_tx(&bars[0], (uint32_t)TiledSmem<D, TILE_WARPS>::JT);
+    tma_load_1d(Jt, soa + (size_t)cb * RN * 32, (uint32_t)TiledSmem<D, TILE_WARPS>::JT, &bars[0]);
     const int rows = min(TILE_WARPS, r_end - r0);
     mbar_expect_tx(&bars[1], (uint32_t)(rows * RN * 8));
     tma_load_1d(It, aos + (size_t)r0 * RN, (uint32_t)(rows * RN * 8), &bars[1]);
@@ -191,6 +190,20 @@ void launch_gather_records(int dim, GroupView g, const double* traj, int k0, dou
   gather_launch(dim, g, traj, k0, aos, soa, st);
 }
 
+int g_tiled_variant = 2; /* 2 = 12 warps x 1 block/SM (default); experiment knobs: 0 = 4 warps x 2 blocks, 1 = 10 x 1, 3 = 8 x 1 */
+
+template <int D, int TW, int MINB>
+static void launch_variant(GroupView g, const double* aos, const double* soa, int j_begin, int cb_begin, dim3 grid, Shard sh,
+                           Thresholds th, Flagged fl, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(pairwise_tiled_kernel<D, TW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)TiledSmem<D, TW>::BYTES);
+    attr = true;
+  }
+  pairwise_tiled_kernel<D, TW, MINB><<<grid, TW * 32, TiledSmem<D, TW>::BYTES, st>>>(g, aos, soa, j_begin, cb_begin, sh, th, fl);
+}
+
 void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, const double* soa, int j_begin, Shard sh,
                            Thresholds th, Flagged fl, cudaStream_t st) {
   (void)mode; /* MODE_PCM only */
@@ -198,20 +211,17 @@ void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, co
   const int cb_begin = j_begin / 32;
   const int cb_end = (g.n + 31) / 32;
   dim3 grid((g.n + TILE_SEG - 1) / TILE_SEG, cb_end - cb_begin);
-  static bool attr3 = false, attr2 = false;
   if (dim == 3) {
-    if (!attr3) {
-      cudaFuncSetAttribute(pairwise_tiled_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TiledSmem<3>::BYTES);
-      attr3 = true;
+    switch (g_tiled_variant) {
+      case 1: launch_variant<3, 10, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st); break;
+      case 3: launch_variant<3, 8, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st); break;
+      case 0: launch_variant<3, 4, 2>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st); break;
+      default: launch_variant<3, 12, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st); break;
     }
-    pairwise_tiled_kernel<3><<<grid, TILE_WARPS * 32, TiledSmem<3>::BYTES, st>>>(g, aos, soa, j_begin, cb_begin, sh, th, fl);
   } else {
-    if (!attr2) {
-      cudaFuncSetAttribute(pairwise_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TiledSmem<2>::BYTES);
-      attr2 = true;
-    }
-    pairwise_tiled_kernel<2><<<grid, TILE_WARPS * 32, TiledSmem<2>::BYTES, st>>>(g, aos, soa, j_begin, cb_begin, sh, th, fl);
+    launch_variant<2, 12, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st);
   }
 }
 
 }  // namespace rpgo
+int g_tiled_variant_set(int v) { rpgo::g_tiled_variant = v; return v; }
