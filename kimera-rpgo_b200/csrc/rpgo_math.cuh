@@ -271,13 +271,21 @@ __host__ __device__ __noinline__ double slow_div(double a, double x) { return a 
 static double slow_div(double a, double x) { return a / x; }
 #endif
 
+/* exponent-range guard evaluated on the integer pipe (device) so that it does not compete for FP64 issue */
+RPGO_FN bool quot_in_safe_range(double q0, double a) {
+#if defined(__CUDA_ARCH__)
+  const int e = (__double2hiint(q0) >> 20) & 0x7ff;
+  return (e > 100 && e < 1900) || a == 0.0;
+#else
+  const double aq = fabs(q0);
+  return (aq > 0x1p-922 && aq < 0x1p+877) || a == 0.0;
+#endif
+}
 RPGO_FN double div_by(double a, double x, double r) {
   const double q0 = a * r;
   const double rem = fma(-q0, x, a);
   double q = fma(rem, r, q0);
-  const double aq = fabs(q0);
-  const bool safe = (aq > 1e-280 && aq < 1e280) || a == 0.0;
-  if (!safe) q = slow_div(a, x); /* rare: one shared out-of-line division */
+  if (!quot_in_safe_range(q0, a)) q = slow_div(a, x); /* rare: one shared out-of-line division */
   return q;
 }
 RPGO_FN bool rcp_safe(double x) {
@@ -422,6 +430,7 @@ RPGO_FN double quad_form_inv(const double* Min, const double* v) {
 template <int N>
 RPGO_FN double quad_form_inv_fast(const double* Min, const double* v) {
   double lu[N * N];
+  double rdiag[N];
   int perm[N];
   RPGO_UNROLL
   for (int i = 0; i < N * N; ++i) lu[i] = Min[i];
@@ -465,8 +474,17 @@ RPGO_FN double quad_form_inv_fast(const double* Min, const double* v) {
         perm[k] = newk;
       }
       const double pv = lu[k * N + k];
-      RPGO_UNROLL
-      for (int i = k + 1; i < N; ++i) lu[i * N + k] = lu[i * N + k] / pv;
+      const double rp = 1.0 / pv; /* shared by this column's divisions and by the back substitution */
+      rdiag[k] = rp;
+      if (rcp_safe(pv)) {
+        RPGO_UNROLL
+        for (int i = k + 1; i < N; ++i) lu[i * N + k] = div_by(lu[i * N + k], pv, rp);
+      } else {
+        RPGO_UNROLL
+        for (int i = k + 1; i < N; ++i) lu[i * N + k] = slow_div(lu[i * N + k], pv);
+      }
+    } else {
+      rdiag[k] = 1.0 / lu[k * N + k]; /* zero pivot column: 1/0 exactly as the plain path computes it */
     }
     RPGO_UNROLL
     for (int i = k + 1; i < N; ++i) {
@@ -474,9 +492,6 @@ RPGO_FN double quad_form_inv_fast(const double* Min, const double* v) {
       for (int j = k + 1; j < N; ++j) lu[i * N + j] = fma(-lu[i * N + k], lu[k * N + j], lu[i * N + j]);
     }
   }
-  double rdiag[N];
-  RPGO_UNROLL
-  for (int i = 0; i < N; ++i) rdiag[i] = 1.0 / lu[i * N + i];
   /* inverse = U^-1 (L^-1 P).  Column c of P is e_p with perm[p] == c, so column c of the inverse is
    * U^-1 applied to column p of L^-1.  L^-1's columns have a static triangular zero pattern (the skipped
    * operations of the dense forward substitution are exact no-ops), so they are built without selects;
@@ -880,7 +895,7 @@ RPGO_FN bool pair_check_v1(const double* Ta, int sa, const double* Tb, int sb, c
     RPGO_UNROLL
     for (int i = 0; i < NN; ++i) x.cov[i] = pT[(OC + i) * stT] - x.cov[i];
     if (!swapped) {
-      if (!llt_ok<N>(x.cov)) {
+      if (!llt_ok_fast<N>(x.cov)) {
         /* failure at a later pivot: rare, divergent slow path, identical to the reference's order */
         const Adj<D> H2 = adjoint<D>(inverse<D>(between<D>(B, A)));
         RPGO_UNROLL
