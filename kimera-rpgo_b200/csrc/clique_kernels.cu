@@ -21,8 +21,10 @@
  * evaluated against a snapshot of maxClq; the first candidate that improves it commits, later
  * candidates are re-evaluated against the new bound (identical to the sequential order of events).
  */
+#include <algorithm>
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "kernels.cuh"
@@ -30,6 +32,7 @@
 namespace rpgo {
 
 static constexpr int HEU_THREADS = 128;
+static constexpr int HEU_PRE = 13; /* words per thread covered by the sweep prefetch (13 * 128 * 32 = 53k vertices) */
 
 __global__ void degmask_kernel(const int32_t* __restrict__ deg, int n, int M, uint32_t* mask, int words) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -63,16 +66,133 @@ __device__ __forceinline__ void block_sum_max(int& s, int& m, int* sh) {
   m = tm;
 }
 
+
+static constexpr int HEU_LIST_K = 4;                       /* list elements per thread */
+static constexpr int HEU_LIST_MAX = HEU_LIST_K * HEU_THREADS;
+
+/* Tail of a greedy chain once at most HEU_LIST_MAX candidates survive: the survivors are written to shared
+ * memory as a list in DESCENDING id order, so that "highest set bit of R" becomes "first live list entry"; each
+ * pick then costs one adjacency word per live entry instead of a sweep over the whole bitset.  Same picks, same
+ * order, same count as the bitset loop.  Returns the number of picks made (-1: a lower candidate already
+ * improved, give up; -2: cannot beat M). */
+__device__ int heu_list_tail(const uint32_t* __restrict__ bits, int64_t stride32, const uint32_t* R, int top, int cnt,
+                             int steps, int M, int v, unsigned long long* ctl, int32_t* my_picks, int32_t* L, int* sh) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  /* build the list: thread t owns the word range [top - (t+1)*C + 1, top - t*C] scanned from the top */
+  const int C = (top + HEU_THREADS) / HEU_THREADS;
+  int mine = 0;
+  for (int c = 0; c < C; ++c) {
+    const int w = top - tid * C - c;
+    if (w >= 0) mine += __popc(R[w]);
+  }
+  /* exclusive prefix over threads (ascending tid = descending ids) */
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  __syncthreads();
+  if (lane == 31) sh[wid] = incl;
+  __syncthreads();
+  int off = incl - mine;
+  for (int i = 0; i < wid; ++i) off += sh[i];
+  for (int c = 0; c < C; ++c) {
+    const int w = top - tid * C - c;
+    if (w >= 0) {
+      uint32_t r = R[w];
+      while (r) {
+        const int b = 31 - __clz(r);
+        r &= ~(1u << b);
+        L[off++] = w * 32 + b;
+      }
+    }
+  }
+  __syncthreads();
+  int u[HEU_LIST_K];
+  bool alive[HEU_LIST_K];
+#pragma unroll
+  for (int k = 0; k < HEU_LIST_K; ++k) {
+    const int pos = k * HEU_THREADS + tid;
+    alive[k] = pos < cnt;
+    u[k] = alive[k] ? L[pos] : 0;
+  }
+  int m = cnt, made = 0, iter = 0;
+  while (m > 0) {
+    if (steps + made + m + 1 <= M) return -2;
+    /* first live entry (block-wide minimum position) and live count */
+    int first = INT_MAX, live = 0;
+#pragma unroll
+    for (int k = 0; k < HEU_LIST_K; ++k) {
+      if (alive[k]) {
+        first = min(first, k * HEU_THREADS + tid);
+        ++live;
+      }
+    }
+    first = __reduce_min_sync(0xffffffffu, first);
+    live = __reduce_add_sync(0xffffffffu, live);
+    __syncthreads();
+    if (lane == 0) {
+      sh[wid] = first;
+      sh[32 + wid] = live;
+    }
+    if (tid == 0) sh[16] = ((++iter & 15) == 0 && (long long)(*(volatile unsigned long long*)ctl >> 32) < (long long)v) ? 1 : 0;
+    __syncthreads();
+    first = INT_MAX;
+    live = 0;
+#pragma unroll
+    for (int i = 0; i < HEU_THREADS / 32; ++i) {
+      first = min(first, sh[i]);
+      live += sh[32 + i];
+    }
+    if (sh[16]) return -1;
+    m = live;
+    if (m == 0) break;
+    if (steps + made + m + 1 <= M) return -2;
+    const int pick = L[first];
+    if (tid == 0) my_picks[steps + made] = pick;
+    ++made;
+    const uint32_t* prow = bits + (size_t)pick * stride32;
+#pragma unroll
+    for (int k = 0; k < HEU_LIST_K; ++k) {
+      if (alive[k]) {
+        const int pos = k * HEU_THREADS + tid;
+        if (pos == first) alive[k] = false;
+        else alive[k] = (prow[u[k] >> 5] >> (u[k] & 31)) & 1u;
+      }
+    }
+    m -= 1; /* refined at the top of the next iteration */
+  }
+  return made;
+}
+
+/* un-mark the cached verdict of every neighbour of the vertices in xs (their filter membership changed) */
+__global__ void undead_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n, const int32_t* __restrict__ xs, int nx,
+                              int32_t* dead_flags) {
+  const int u = xs[blockIdx.x];
+  const int W = (n + 31) / 32;
+  for (int w = threadIdx.x; w < W; w += blockDim.x) {
+    uint32_t r = bits[(size_t)u * stride32 + w];
+    while (r) {
+      const int b = __ffs(r) - 1;
+      r &= r - 1;
+      dead_flags[w * 32 + b] = 0;
+    }
+  }
+  if (threadIdx.x == 0) dead_flags[u] = 0;
+}
+
 /* ctl[0]: packed (candidate << 32 | icc) of the lowest-index improving candidate of this round
  *         (ULLONG_MAX = none).  picks_block: per-block pick log (n ints each). */
 __global__ void __launch_bounds__(HEU_THREADS) heu_round_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n,
                                                                 const int32_t* __restrict__ deg,
                                                                 const uint32_t* __restrict__ degmask, int first, int M,
-                                                                unsigned long long* ctl, int32_t* picks_block) {
+                                                                unsigned long long* ctl, int32_t* picks_block,
+                                                                int32_t* dead_flags) {
   extern __shared__ uint32_t R[];
   __shared__ int sh[64];
-  __shared__ uint32_t s_P;
   __shared__ int s_abort;
+  __shared__ int32_t s_list[HEU_LIST_MAX];
   const int W = (n + 31) / 32;
   const int tid = threadIdx.x;
   int32_t* my_picks = picks_block + (size_t)blockIdx.x * n;
@@ -84,6 +204,7 @@ __global__ void __launch_bounds__(HEU_THREADS) heu_round_kernel(const uint32_t* 
     __syncthreads();
     if (s_abort) return;
     if (M > deg[v]) continue; /* pruning 1 */
+    if (dead_flags[v]) continue; /* evaluated under an equivalent bound before: cannot improve (see host driver) */
     int cnt = 0, top = -1;
     for (int w = tid; w < W; w += blockDim.x) {
       const uint32_t r = bits[(size_t)v * stride32 + w] & degmask[w];
@@ -92,62 +213,120 @@ __global__ void __launch_bounds__(HEU_THREADS) heu_round_kernel(const uint32_t* 
       if (r) top = w;
     }
     block_sum_max(cnt, top, sh);
-    if (cnt + 1 <= M) continue; /* cannot exceed the bound */
+    if (cnt + 1 <= M) {
+      if (tid == 0) dead_flags[v] = 1;
+      continue; /* cannot exceed the bound */
+    }
+#ifdef RPGO_CLIQUE_COUNTERS
+    if (tid == 0) atomicAdd(ctl + 1, 1ULL);
+#endif
     int steps = 0;
     bool dead = false;
     int iter = 0;
     while (cnt > 0) {
       if (steps + cnt + 1 <= M) { dead = true; break; }
+      if (cnt <= HEU_LIST_MAX) {
+        const int made = heu_list_tail(bits, stride32, R, top, cnt, steps, M, v, ctl, my_picks, s_list, sh);
+        if (made == -1) return;
+        if (made == -2) { dead = true; break; }
+        steps += made;
+        break;
+      }
       if (tid == 0) s_abort = ((++iter & 7) == 0 && (long long)(*(volatile unsigned long long*)ctl >> 32) < (long long)v) ? 1 : 0;
       const int t = top;
-      if (tid < 32) {
-        const uint32_t T = R[t];
-        const int lane = tid;
-        uint32_t rw = 0;
-        if ((T >> lane) & 1u) rw = bits[(size_t)(t * 32 + lane) * stride32 + t];
-        uint32_t cur = T, P = 0;
-        int k = 0;
-        while (cur) {
-          const int b = 31 - __clz(cur);
-          P |= 1u << b;
-          const uint32_t rb = __shfl_sync(0xffffffffu, rw, b);
-          cur &= rb & ~(1u << b);
-          if (lane == 0) my_picks[steps + k] = t * 32 + b;
-          ++k;
-        }
-        if (lane == 0) {
-          s_P = P;
-          R[t] = 0;
+#ifdef RPGO_CLIQUE_COUNTERS
+      if (tid == 0) atomicAdd(ctl + 2, 1ULL);
+#endif
+      const uint32_t T = R[t];
+      const int lane = tid & 31;
+      /* every warp resolves the window redundantly from the same 32x32 adjacency block (no block barrier
+       * between resolution and sweep), and the sweep's row words are requested BEFORE the resolution so
+       * that both dependent global accesses overlap: one memory round trip per window */
+      uint32_t rw = 0;
+      if ((T >> lane) & 1u) rw = bits[(size_t)(t * 32 + lane) * stride32 + t];
+      const int nT = __popc(T);
+      uint32_t pre[4][HEU_PRE]; /* up to 4 candidate rows x HEU_PRE words per thread are prefetched */
+      const bool prefetch = (nT <= 4) && (t <= HEU_PRE * HEU_THREADS);
+      if (prefetch) {
+        uint32_t q = T;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int b = q ? 31 - __clz(q) : -1;
+          if (b >= 0) q &= ~(1u << b);
+#pragma unroll
+          for (int k = 0; k < HEU_PRE; ++k) {
+            const int w = tid + k * HEU_THREADS;
+            pre[c][k] = (b >= 0 && w < t) ? bits[(size_t)(t * 32 + b) * stride32 + w] : 0xffffffffu;
+          }
         }
       }
-      __syncthreads();
+      uint32_t cur = T, P = 0;
+      int k0 = 0;
+      while (cur) {
+        const int b = 31 - __clz(cur);
+        P |= 1u << b;
+        const uint32_t rb = __shfl_sync(0xffffffffu, rw, b);
+        cur &= rb & ~(1u << b);
+        if (tid == 0) my_picks[steps + k0] = t * 32 + b;
+        ++k0;
+      }
+      __syncthreads(); /* all warps have read R[t] / s_abort is visible */
       if (s_abort) return;
-      const uint32_t P = s_P;
+      if (tid == 0) R[t] = 0;
       steps += __popc(P);
       cnt = 0;
       top = -1;
-      for (int w = tid; w < t; w += blockDim.x) {
-        uint32_t r = R[w];
-        if (r) {
-          uint32_t q = P;
-          while (q && r) {
-            const int b = 31 - __clz(q);
-            q &= ~(1u << b);
-            r &= bits[(size_t)(t * 32 + b) * stride32 + w];
+      if (prefetch) {
+        /* AND mask of the candidate rows that turned out to be picks */
+#pragma unroll
+        for (int k = 0; k < HEU_PRE; ++k) {
+          const int w = tid + k * HEU_THREADS;
+          if (w < t) {
+            uint32_t r = R[w];
+            if (r) {
+              uint32_t q = T;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const int b = q ? 31 - __clz(q) : -1;
+                if (b >= 0) {
+                  q &= ~(1u << b);
+                  if ((P >> b) & 1u) r &= pre[c][k];
+                }
+              }
+              R[w] = r;
+              cnt += __popc(r);
+              if (r) top = w;
+            }
           }
-          R[w] = r;
-          cnt += __popc(r);
-          if (r) top = w;
+        }
+      } else {
+        for (int w = tid; w < t; w += blockDim.x) {
+          uint32_t r = R[w];
+          if (r) {
+            uint32_t q = P;
+            while (q && r) {
+              const int b = 31 - __clz(q);
+              q &= ~(1u << b);
+              r &= bits[(size_t)(t * 32 + b) * stride32 + w];
+            }
+            R[w] = r;
+            cnt += __popc(r);
+            if (r) top = w;
+          }
         }
       }
       block_sum_max(cnt, top, sh);
     }
-    if (dead) continue;
+    if (dead) {
+      if (tid == 0) dead_flags[v] = 1;
+      continue;
+    }
     const int icc = steps + 1;
     if (icc > M) {
       if (tid == 0) atomicMin(ctl, ((unsigned long long)(unsigned)v << 32) | (unsigned)icc);
       return; /* later candidates of this block are > v: re-evaluated next round */
     }
+    if (tid == 0) dead_flags[v] = 1; /* completed chain that did not beat M */
   }
 }
 
@@ -233,6 +412,17 @@ int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_
     cudaFuncSetAttribute(heu_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
+  /* "dead" cache: a candidate that could not beat bound M cannot beat any M' >= M as long as its filtered
+   * neighbourhood {u : deg(u) >= M} is unchanged, i.e. as long as no vertex has M <= deg < M'.  The host checks
+   * that on the sorted degree list at every bound change and clears the cache otherwise. */
+  std::vector<int32_t> hdeg(n);
+  CUCHECK(cudaMemcpyAsync(hdeg.data(), deg, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  CUCHECK(cudaMemsetAsync(s.elim, 0, sizeof(int32_t) * n, st));
+  CUCHECK(cudaStreamSynchronize(st));
+  /* vertices sorted by degree, for the "whose filter membership changes between M and M'" query */
+  std::vector<int32_t> by_deg(n);
+  for (int i = 0; i < n; ++i) by_deg[i] = i;
+  std::sort(by_deg.begin(), by_deg.end(), [&](int a, int b) { return hdeg[a] < hdeg[b]; });
   int M = maxclq0;
   int winner = -1, winner_M = 0, winner_icc = 0, winner_block = 0;
   int start = first < 0 ? 0 : first;
@@ -241,15 +431,22 @@ int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_
   unsigned long long h_ctl;
   while (start < n) {
     const unsigned long long none = ~0ULL;
-    CUCHECK(cudaMemcpyAsync(s.ctl, &none, sizeof(none), cudaMemcpyHostToDevice, st));
+    const unsigned long long init3[3] = {none, 0ULL, 0ULL};
+    CUCHECK(cudaMemcpyAsync(s.ctl, init3, sizeof(init3), cudaMemcpyHostToDevice, st));
     degmask_kernel<<<(W + 127) / 128, 128, 0, st>>>(deg, n, M, s.degmask, W);
     int grid = n - start;
     if (grid > grid_cap) grid = grid_cap;
     heu_round_kernel<<<grid, HEU_THREADS, smem, st>>>(bits, stride32, n, deg, s.degmask, start, M,
-                                                      (unsigned long long*)s.ctl, (int32_t*)s.rwork);
+                                                      (unsigned long long*)s.ctl, (int32_t*)s.rwork, s.elim);
     *launches += 2;
     CUCHECK(cudaMemcpyAsync(&h_ctl, s.ctl, sizeof(h_ctl), cudaMemcpyDeviceToHost, st));
     CUCHECK(cudaStreamSynchronize(st));
+    if (getenv("RPGO_CLIQUE_TRACE")) {
+      unsigned long long c[3];
+      cudaMemcpy(c, s.ctl, sizeof(c), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[clique] round start=%d M=%d grid=%d -> improver=%lld icc=%d | chains started %llu, windows %llu\n", start, M, grid,
+              h_ctl == none ? -1LL : (long long)(h_ctl >> 32), (int)(h_ctl & 0xffffffffu), c[1], c[2]);
+    }
     if (h_ctl == none) break;
     winner = (int)(h_ctl >> 32);
     winner_icc = (int)(h_ctl & 0xffffffffu);
@@ -258,6 +455,20 @@ int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_
     /* keep the winner's pick log (its block may be reused next round) */
     CUCHECK(cudaMemcpyAsync(s.picks, (int32_t*)s.rwork + (size_t)winner_block * n,
                             sizeof(int32_t) * (size_t)(winner_icc - 1 > 0 ? winner_icc - 1 : 0), cudaMemcpyDeviceToDevice, st));
+    {
+      /* any vertex with M <= deg < winner_icc changes the filter: cached verdicts are no longer valid */
+      auto lo = std::lower_bound(by_deg.begin(), by_deg.end(), M, [&](int a, int val) { return hdeg[a] < val; });
+      auto hi = std::lower_bound(by_deg.begin(), by_deg.end(), winner_icc, [&](int a, int val) { return hdeg[a] < val; });
+      const int nx = (int)(hi - lo);
+      if (nx > 4096) {
+        CUCHECK(cudaMemsetAsync(s.elim, 0, sizeof(int32_t) * n, st));
+      } else if (nx > 0) {
+        /* only candidates adjacent to one of those vertices see a different filtered neighbourhood */
+        CUCHECK(cudaMemcpyAsync(s.result, &*lo, sizeof(int32_t) * nx, cudaMemcpyHostToDevice, st));
+        undead_kernel<<<nx, 128, 0, st>>>(bits, stride32, n, s.result, nx, s.elim);
+        *launches += 1;
+      }
+    }
     M = winner_icc;
     start = winner + 1;
   }
