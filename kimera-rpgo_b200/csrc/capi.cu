@@ -28,32 +28,57 @@ using namespace rpgo;
 
 namespace {
 
+/* Device memory comes from a per-handle bump arena whose chunks are taken from CUDA's stream-ordered pool
+ * (cudaMallocAsync; the pool keeps freed chunks cached, so the next handle of the process re-uses them):
+ * a PCM session makes hundreds of small growing allocations (36 groups x 10 arrays) and plain cudaMalloc
+ * costs milliseconds each on this platform. */
+struct Arena {
+  struct Chunk { char* p; size_t cap, used; };
+  std::vector<Chunk> chunks;
+  cudaStream_t st = nullptr;
+  static constexpr size_t CHUNK = (size_t)64 << 20;
+  void* alloc(size_t bytes) {
+    bytes = (bytes + 255) & ~size_t(255);
+    if (!chunks.empty() && chunks.back().used + bytes <= chunks.back().cap) {
+      void* r = chunks.back().p + chunks.back().used;
+      chunks.back().used += bytes;
+      return r;
+    }
+    const size_t cap = bytes > CHUNK ? bytes : CHUNK;
+    void* p = nullptr;
+    if (cudaMallocAsync(&p, cap, st) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    /* keep the partially used previous chunk reachable for small requests: put the big one first */
+    Chunk c{(char*)p, cap, bytes};
+    if (bytes > CHUNK / 2 && !chunks.empty()) chunks.insert(chunks.end() - 1, c);
+    else chunks.push_back(c);
+    return p;
+  }
+  void release() {
+    for (auto& c : chunks) cudaFreeAsync(c.p, st);
+    chunks.clear();
+  }
+};
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
-  ~DevBuf() { release(); }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-  }
-  /* grow to at least `bytes`; optionally keep the first `keep` bytes; new memory is zeroed */
+  Arena* arena = nullptr;
+  /* grow to at least `bytes`; optionally keep the first `keep` bytes; new memory is zeroed.  The old block
+   * stays in the arena until the handle dies (growth is geometric, so at most 2x is held). */
   cudaError_t ensure(size_t bytes, size_t keep, cudaStream_t st) {
     if (bytes <= cap) return cudaSuccess;
     size_t ncap = std::max(bytes, cap * 2);
     ncap = (ncap + 255) & ~size_t(255);
-    void* np = nullptr;
-    cudaError_t e = cudaMalloc(&np, ncap);
-    if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(np, 0, ncap, st);
+    void* np = arena->alloc(ncap);
+    if (!np) return cudaErrorMemoryAllocation;
+    cudaError_t e = cudaMemsetAsync(np, 0, ncap, st);
     if (e != cudaSuccess) return e;
     if (p && keep) {
       e = cudaMemcpyAsync(np, p, std::min(keep, cap), cudaMemcpyDeviceToDevice, st);
       if (e != cudaSuccess) return e;
-    }
-    if (p) {
-      cudaStreamSynchronize(st);
-      cudaFree(p);
     }
     p = np;
     cap = ncap;
@@ -87,6 +112,9 @@ struct Group {
   std::vector<uint64_t> kfrom, kto;
   std::vector<int32_t> h_idxf, h_idxb;
   std::vector<uint8_t> h_pfx;
+  explicit Group(Arena* a) {
+    for (DevBuf* b : {&lc, &idxf, &idxb, &pfx, &bits, &deg, &fl_pairs, &fl_count, &rec_aos, &rec_soa}) b->arena = a;
+  }
 };
 
 constexpr int64_t FLAG_CAP = 1 << 20;
@@ -99,6 +127,7 @@ PinBuf& pinned_staging() {
 }  // namespace
 
 struct rpgo_handle {
+  Arena arena;
   rpgo_cfg cfg;
   int dim = 3, mode = 0, E = 50, PS = 12, NN = 36;
   bool odom_check = true, loop_check = true;
@@ -120,13 +149,22 @@ struct rpgo_handle {
 
   /* staging (the pinned host buffer is per thread, shared by successive handles: cudaMallocHost is slow) */
   DevBuf d_stage;
-  DevBuf d_lcent, d_ok, d_dist;
+  DevBuf d_lcent, d_ok, d_dist, d_scan;
   /* clique scratch */
   DevBuf c_degmask, c_picks, c_elim, c_result, c_ctl, c_rwork;
 
+  void wire() {
+    arena.st = stream;
+    for (DevBuf* b : {&traj, &d_stage, &d_lcent, &d_ok, &d_dist, &d_scan, &c_degmask, &c_picks, &c_elim, &c_result, &c_ctl, &c_rwork})
+      b->arena = &arena;
+  }
   ~rpgo_handle() {
     for (Group* g : groups) delete g;
-    if (stream) cudaStreamDestroy(stream);
+    if (stream) {
+      arena.release();
+      cudaStreamSynchronize(stream);
+      cudaStreamDestroy(stream);
+    }
   }
 };
 
@@ -195,17 +233,13 @@ static int ensure_group(rpgo_handle* h, Group* g, int64_t need) {
     const int64_t nstride = ncap / 32;
     /* in multi-GPU mode rows are padded to 2*world chunks */
     const int64_t rows = ncap + 64 * (int64_t)std::max(1, h->cfg.world);
-    void* nb = nullptr;
     const size_t bytes = (size_t)rows * nstride * 4;
-    H_CHECK_CUDA(h, cudaMalloc(&nb, bytes));
+    void* nb = h->arena.alloc(bytes);
+    if (!nb) { h->err = "device allocation failed (adjacency)"; return RPGO_ERR_NOMEM; }
     H_CHECK_CUDA(h, cudaMemsetAsync(nb, 0, bytes, st));
     if (g->bits.p && g->n > 0)
       H_CHECK_CUDA(h, cudaMemcpy2DAsync(nb, (size_t)nstride * 4, g->bits.p, (size_t)g->stride32 * 4,
                                         (size_t)((g->n + 31) / 32) * 4, (size_t)g->n, cudaMemcpyDeviceToDevice, st));
-    if (g->bits.p) {
-      H_CHECK_CUDA(h, cudaStreamSynchronize(st));
-      cudaFree(g->bits.p);
-    }
     g->bits.p = nb;
     g->bits.cap = bytes;
     g->stride32 = nstride;
@@ -327,6 +361,17 @@ int rpgo_create(const rpgo_cfg* cfg, rpgo_handle** out) {
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
     return RPGO_ERR_CUDA;
+  }
+  h->wire();
+  {
+    /* keep freed arena chunks cached in the device's default pool across handles */
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t thr = ~0ULL;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
   }
   /* entry 0 = default T: identity pose, zero covariance, node 0, rotation_info true */
   if (h->traj.ensure((size_t)1024 * h->E * sizeof(double), 0, h->stream) != cudaSuccess) {
@@ -505,7 +550,7 @@ int rpgo_odom_append(rpgo_handle* h, int64_t n, const uint64_t* prev_key, const 
     const int total_chunks = (int)chunk_chain.size();
     const size_t ib = ((size_t)total_chunks * 2 + nch + n) * 4;
     const size_t ib_al = (ib + 15) & ~size_t(15);
-    static thread_local DevBuf scan_buf;
+    DevBuf& scan_buf = h->d_scan;
     H_CHECK_CUDA(h, scan_buf.ensure(ib_al + (size_t)total_chunks * E * 8, 0, st));
     std::vector<int32_t> ints;
     ints.insert(ints.end(), chunk_chain.begin(), chunk_chain.end());
@@ -634,7 +679,7 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
     int32_t gi;
     auto it = h->gindex.find(id);
     if (it == h->gindex.end()) {
-      Group* g = new Group();
+      Group* g = new Group(&h->arena);
       g->id1 = id.first;
       g->id2 = id.second;
       gi = (int32_t)h->groups.size();
@@ -852,8 +897,15 @@ int rpgo_pair_distances(rpgo_handle* h, int32_t gi, double* dist_out) {
   Group* g = h->groups[gi];
   const int64_t n = g->n;
   if (n > 8192) { h->err = "pair_distances is a debug call: n <= 8192"; return RPGO_ERR_INVALID; }
-  DevBuf dd;
-  H_CHECK_CUDA(h, dd.ensure((size_t)n * n * 8, 0, h->stream));
+  /* debug buffer: allocated and freed directly (not from the arena, which never releases) */
+  struct Tmp {
+    double* p = nullptr;
+    cudaStream_t st;
+    ~Tmp() { if (p) cudaFreeAsync(p, st); }
+    double* as() { return p; }
+  } dd;
+  dd.st = h->stream;
+  H_CHECK_CUDA(h, cudaMallocAsync((void**)&dd.p, std::max<size_t>((size_t)n * n * 8, 8), h->stream));
   /* count is reset so that the recompute does not double-count flagged pairs */
   unsigned long long saved = 0;
   if (g->fl_count.p) H_CHECK_CUDA(h, cudaMemcpyAsync(&saved, g->fl_count.p, 8, cudaMemcpyDeviceToHost, h->stream));
@@ -861,7 +913,7 @@ int rpgo_pair_distances(rpgo_handle* h, int32_t gi, double* dist_out) {
   /* force all rows: temporarily single-GPU sharding */
   const int w = h->cfg.world, r = h->cfg.rank;
   h->cfg.world = 1; h->cfg.rank = 0;
-  int rc = run_pairwise(h, g, 0, dd.as<double>());
+  int rc = run_pairwise(h, g, 0, dd.as());
   h->cfg.world = w; h->cfg.rank = r;
   if (rc != RPGO_OK) return rc;
   if (g->fl_count.p) H_CHECK_CUDA(h, cudaMemcpyAsync(g->fl_count.p, &saved, 8, cudaMemcpyHostToDevice, h->stream));
@@ -914,7 +966,7 @@ int rpgo_debug_load_group(rpgo_handle* h, uint8_t id1, uint8_t id2, int64_t n, c
   int32_t gi;
   auto it = h->gindex.find(id);
   if (it == h->gindex.end()) {
-    Group* g = new Group();
+    Group* g = new Group(&h->arena);
     g->id1 = id.first;
     g->id2 = id.second;
     gi = (int32_t)h->groups.size();
