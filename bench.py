@@ -175,6 +175,7 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=device)
     assert world == a.gpus or world == 1, "launch with torch.distributed.run for --gpus > 1"
 

@@ -319,3 +319,46 @@ def test_clique_exact_planted():
     gi = g.load_adjacency(a)
     size, ids, _ = g.find_inliers_raw(gi, pkg.CLIQUE_EXACT)
     assert size == k and ids.tolist() == members.tolist()
+
+
+@pytest.mark.parametrize("name", ["ordered", "unordered", "robot_a", "robot_b"])
+def test_g2o_fixtures_on_gpu(name):
+    """the reference's four g2o fixtures (tests/data/*.g2o) through both implementations, three configurations."""
+    values, edges = scenarios.g2o_fixture(name)
+    for mode, params in [(0, dict(odom_threshold=1.0, lc_threshold=1.0)),
+                         (0, dict(odom_threshold=100.0, lc_threshold=100.0)),
+                         (1, dict(odom_trans=0.05, odom_rot=0.01, dist_trans=0.05, dist_rot=0.01))]:
+        o, g = run_both(3, mode, params, [(edges, values)])
+        compare_groups(o, g)
+
+
+def test_abi_error_behaviour():
+    """status codes instead of exceptions / crashes (the reference logs a warning and continues)."""
+    import ctypes as C
+    g = PcmGpu(3, 0)
+    lib, h = g.lib, g.h
+    assert lib.rpgo_odom_append(h, 0, None, None, None, None, None) == 0          # empty batch is fine
+    assert lib.rpgo_odom_append(h, 3, None, None, None, None, None) == 1          # RPGO_ERR_INVALID
+    assert lib.rpgo_lc_append(h, 2, None, None, None, None, None, None, None, None) == 1
+    size = C.c_int64()
+    ids = (C.c_int32 * 4)()
+    assert lib.rpgo_find_inliers(h, 7, 0, 0, 0, ids, C.byref(size), None) == 4    # RPGO_ERR_NOT_FOUND
+    assert lib.rpgo_lc_remove_last(h, 0, None, None) == 4
+    assert lib.rpgo_find_group(h, ord('a'), ord('b')) == -1
+    assert g.remove_last() is None and g.remove_last('a', 'b') is None           # nothing to remove -> null edge
+    assert g.update([], []) is False
+    cfg = pkg._capi.RpgoCfg()
+    lib.rpgo_default_cfg(C.byref(cfg))
+    cfg.dim = 5
+    hh = C.c_void_p()
+    assert lib.rpgo_create(C.byref(cfg), C.byref(hh)) == 1
+
+
+def test_single_closure_and_disabled_checks():
+    """n = 1 groups (1x1 zero adjacency => clique size 1, id 0) and the 'threshold < 0 disables' rules (Pcm.h:74-82)."""
+    gph = synth.config2(seed=17, P=120, n=12, outlier_frac=0.5)
+    for params in [dict(odom_threshold=-1, lc_threshold=-1), dict(odom_threshold=5.0, lc_threshold=-1),
+                   dict(odom_threshold=-1, lc_threshold=1e-6)]:
+        calls = [(gph["odom"], gph["values"])] + [([lc], []) for lc in gph["lcs"]]
+        o, g = run_both(3, 0, params, calls)
+        assert o.num_inliers() == g.num_inliers()
