@@ -168,6 +168,10 @@ int rpgo_fp64_peak(int32_t device, double* tflops_out);
 int rpgo_debug_load_group(rpgo_handle* h, uint8_t id1, uint8_t id2, int64_t n, const uint64_t* rows,
                           int64_t stride_words, int32_t* group_out);
 
+/* test hook: compare the branch-free reciprocal / division / square-root sequences used by the straight-line
+ * pair kernel with the built-in IEEE operations on n random operand pairs; *mismatches must come back 0 */
+int rpgo_debug_check_fastmath(int64_t n, uint64_t seed, uint64_t* mismatches, uint64_t* checked);
+
 const char* rpgo_version(void);
 
 #ifdef __cplusplus

@@ -54,6 +54,7 @@ SYMBOLS = [
     ("rpgo_launch_count", C.c_int64, [C.c_void_p]),
     ("rpgo_fp64_peak", C.c_int, [C.c_int32, c_dp]),
     ("rpgo_debug_load_group", C.c_int, [C.c_void_p, C.c_uint8, C.c_uint8, C.c_int64, c_u64p, C.c_int64, c_i32p]),
+    ("rpgo_debug_check_fastmath", C.c_int, [C.c_int64, C.c_uint64, c_u64p, c_u64p]),
     ("rpgo_version", C.c_char_p, []),
 ]
 

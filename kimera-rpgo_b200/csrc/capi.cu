@@ -270,8 +270,8 @@ static int run_pairwise(rpgo_handle* h, Group* g, int64_t j_begin, double* dist_
     extern int g_tiled_variant_set(int);
     g_direct_minb_set(kernel == 13 ? 3 : kernel == 14 ? 4 : 2);
     if (kernel == 13 || kernel == 14) kernel = RPGO_KERNEL_DIRECT;
-    g_tiled_variant_set(kernel >= 20 && kernel <= 23 ? kernel - 20 : 2);
-    if (kernel >= 20 && kernel <= 23) kernel = RPGO_KERNEL_TILED;
+    g_tiled_variant_set(kernel >= 20 && kernel <= 24 ? kernel - 20 : 4);
+    if (kernel >= 20 && kernel <= 24) kernel = RPGO_KERNEL_TILED;
   }
   if (dist_dev) kernel = RPGO_KERNEL_DIRECT;
   if (kernel == RPGO_KERNEL_AUTO) kernel = (h->mode == MODE_PCM) ? RPGO_KERNEL_TILED : RPGO_KERNEL_DIRECT;
@@ -995,6 +995,17 @@ int rpgo_debug_load_group(rpgo_handle* h, uint8_t id1, uint8_t id2, int64_t n, c
   H_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
   if (group_out) *group_out = gi;
   return RPGO_OK;
+}
+
+int rpgo_debug_check_fastmath(int64_t n, uint64_t seed, uint64_t* mismatches, uint64_t* checked) {
+  if (!mismatches || !checked || n <= 0) return RPGO_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return RPGO_ERR_CUDA;
+  unsigned long long m = 0, c = 0;
+  const int rc = fastmath_check((long long)n, (unsigned long long)seed, &m, &c, 0);
+  *mismatches = m;
+  *checked = c;
+  return rc == 0 ? RPGO_OK : RPGO_ERR_CUDA;
 }
 
 int rpgo_fp64_peak(int32_t device, double* tflops_out) {

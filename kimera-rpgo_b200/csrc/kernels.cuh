@@ -83,5 +83,7 @@ int clique_exact(const uint32_t* bits, int64_t stride32, int n, const int32_t* d
                  int32_t* ids_out_host, int64_t* launches, cudaStream_t st);
 
 double fp64_peak_tflops(cudaStream_t st);
+int fastmath_check(long long n, unsigned long long seed, unsigned long long* mismatches, unsigned long long* checked,
+                   cudaStream_t st);
 
 }  // namespace rpgo

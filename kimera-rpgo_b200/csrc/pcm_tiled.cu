@@ -19,6 +19,7 @@
 
 #define RPGO_MATH_IMPL
 #include "kernels.cuh"
+#include "rpgo_pair_v2.cuh"
 
 namespace rpgo {
 
@@ -81,6 +82,14 @@ __device__ __forceinline__ bool row_owned_t(const Shard& sh, int i) {
   return c == sh.rank || c == 2 * (int64_t)sh.world - 1 - sh.rank;
 }
 
+/* exact general path for the rare lanes the straight-line code flags (kept out of line: cold code) */
+template <int D>
+__device__ __noinline__ bool pair_check_exact(const double* Ta, int sa, const double* Tb, int sb, const double* lci, int sli,
+                                              const double* Tc, int sc, const double* Td, int sd, const double* lcj, int slj,
+                                              double* scr, int ss, const Thresholds* th, double* dist, bool* near) {
+  return pair_check_v1<D>(Ta, sa, Tb, sb, lci, sli, Tc, sc, Td, sd, lcj, slj, scr, ss, *th, dist, near);
+}
+
 constexpr int TILE_SEG = 512;   /* rows per work item */
 
 template <int D, int TILE_WARPS>
@@ -92,7 +101,7 @@ struct TiledSmem {
   static constexpr size_t BYTES = JT + IT + SCR + 64;
 };
 
-template <int D, int TILE_WARPS, int MINB>
+template <int D, int TILE_WARPS, int MINB, int PAIRFN>
 __global__ void __launch_bounds__(TILE_WARPS * 32, MINB)
     pairwise_tiled_kernel(GroupView g, const double* __restrict__ aos, const double* __restrict__ soa, int j_begin,
                           int cb_begin, Shard sh, Thresholds th, Flagged fl) {
@@ -158,8 +167,17 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, MINB)
         const double* Td = (pa != pc) ? Jl + Rec<D>::OFF_TF * 32 : Jl + Rec<D>::OFF_TB * 32;
         double dist;
         bool near;
-        ok = pair_check_v1<D>(Ir + Rec<D>::OFF_TF, 1, Ir + Rec<D>::OFF_TB, 1, Ir + Rec<D>::OFF_LC, 1, Tc, 32, Td, 32,
-                              Jl + Rec<D>::OFF_LC * 32, 32, scr, TILE_WARPS * 32, th, &dist, &near);
+        if (PAIRFN == 2) {
+          bool bad;
+          ok = pair_check_v2<D>(Ir + Rec<D>::OFF_TF, 1, Ir + Rec<D>::OFF_TB, 1, Ir + Rec<D>::OFF_LC, 1, Tc, 32, Td, 32,
+                                Jl + Rec<D>::OFF_LC * 32, 32, scr, TILE_WARPS * 32, th, &dist, &near, &bad);
+          if (bad)
+            ok = pair_check_exact<D>(Ir + Rec<D>::OFF_TF, 1, Ir + Rec<D>::OFF_TB, 1, Ir + Rec<D>::OFF_LC, 1, Tc, 32, Td, 32,
+                                     Jl + Rec<D>::OFF_LC * 32, 32, scr, TILE_WARPS * 32, &th, &dist, &near);
+        } else {
+          ok = pair_check_v1<D>(Ir + Rec<D>::OFF_TF, 1, Ir + Rec<D>::OFF_TB, 1, Ir + Rec<D>::OFF_LC, 1, Tc, 32, Td, 32,
+                                Jl + Rec<D>::OFF_LC * 32, 32, scr, TILE_WARPS * 32, th, &dist, &near);
+        }
         if (near) {
           const unsigned long long slot = atomicAdd(fl.count, 1ULL);
           if ((int64_t)slot < fl.cap) {
@@ -190,18 +208,70 @@ void launch_gather_records(int dim, GroupView g, const double* traj, int k0, dou
   gather_launch(dim, g, traj, k0, aos, soa, st);
 }
 
-int g_tiled_variant = 2; /* 2 = 12 warps x 1 block/SM (default); experiment knobs: 0 = 4 warps x 2 blocks, 1 = 10 x 1, 3 = 8 x 1 */
+/* ---- validation of the straight-line operations against the built-in IEEE ones (debug hook) -------------- */
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z += 0x9e3779b97f4a7c15ULL;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+  return z ^ (z >> 31);
+}
+__global__ void fastmath_check_kernel(unsigned long long seed, long long per_thread, unsigned long long* mismatches,
+                                      unsigned long long* checked) {
+  const unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long bad_cnt = 0, ok_cnt = 0;
+  for (long long it = 0; it < per_thread; ++it) {
+    const unsigned long long r1 = mix64(seed + gid * 0x100000001b3ULL + (unsigned long long)it * 2ULL);
+    const unsigned long long r2 = mix64(r1);
+    /* random sign/mantissa, exponent spread over 2^-300 .. 2^300 (mostly) with occasional extremes */
+    const int e1 = (int)((r1 >> 52) % 640) - 320, e2 = (int)((r2 >> 52) % 640) - 320;
+    double a = __longlong_as_double((long long)((r1 & 0x800fffffffffffffULL) | ((unsigned long long)(1023 + e1) << 52)));
+    double x = __longlong_as_double((long long)((r2 & 0x800fffffffffffffULL) | ((unsigned long long)(1023 + e2) << 52)));
+    if ((it & 15) == 0) a = __longlong_as_double((long long)((r1 & 0x8000000000000fffULL) | 0x3ff0000000000000ULL)); /* near 1 */
+    if ((it & 31) == 1) x = __longlong_as_double((long long)((r2 | 0x000ffffffffff000ULL) & 0x800fffffffffffffULL | 0x3ff0000000000000ULL)); /* near 2 */
+    bool b1 = false, b2 = false, b3 = false;
+    const double r = opt_rcp(x, b1);
+    const double q = opt_div_by(a, x, r, b2);
+    b2 = b2 || b1;
+    const double ax = fabs(a);
+    const double sq = opt_sqrt(ax, b3);
+    if (!b1) { if (r != 1.0 / x) { ++bad_cnt; atomicAdd(mismatches + 2, 1ULL); } else ++ok_cnt; }
+    if (!b2) { if (q != a / x) { ++bad_cnt; atomicAdd(mismatches + 3, 1ULL); } else ++ok_cnt; }
+    if (!b3) { if (sq != sqrt(ax)) { ++bad_cnt; if (atomicAdd(mismatches + 4, 1ULL) == 0) { mismatches[5] = (unsigned long long)__double_as_longlong(ax); } } else ++ok_cnt; }
+  }
+  atomicAdd(mismatches, bad_cnt);
+  atomicAdd(checked, ok_cnt + bad_cnt);
+}
 
-template <int D, int TW, int MINB>
+int fastmath_check(long long n, unsigned long long seed, unsigned long long* mismatches, unsigned long long* checked,
+                   cudaStream_t st) {
+  unsigned long long* d = nullptr;
+  if (cudaMalloc(&d, 64) != cudaSuccess) return -1;
+  cudaMemsetAsync(d, 0, 64, st);
+  const int threads = 256, blocks = 148 * 8;
+  const long long per_thread = (n + (long long)threads * blocks - 1) / ((long long)threads * blocks);
+  fastmath_check_kernel<<<blocks, threads, 0, st>>>(seed, per_thread, d, d + 1);
+  unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaMemcpyAsync(h, d, 64, cudaMemcpyDeviceToHost, st);
+  cudaStreamSynchronize(st);
+  cudaFree(d);
+  *mismatches = h[0];
+  *checked = h[1];
+  if (h[0]) fprintf(stderr, "[fastmath] mismatches: rcp %llu div %llu sqrt %llu (first sqrt operand bits 0x%016llx)\n", h[2], h[3], h[4], h[5]);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int g_tiled_variant = 4; /* 4 = 12 warps x 1 block/SM, straight-line pair function (default); 2 = same with pair_check_v1; experiment knobs: 0 = 4 warps x 2 blocks, 1 = 10 x 1, 3 = 8 x 1 */
+
+template <int D, int TW, int MINB, int PAIRFN>
 static void launch_variant(GroupView g, const double* aos, const double* soa, int j_begin, int cb_begin, dim3 grid, Shard sh,
                            Thresholds th, Flagged fl, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(pairwise_tiled_kernel<D, TW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(pairwise_tiled_kernel<D, TW, MINB, PAIRFN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)TiledSmem<D, TW>::BYTES);
     attr = true;
   }
-  pairwise_tiled_kernel<D, TW, MINB><<<grid, TW * 32, TiledSmem<D, TW>::BYTES, st>>>(g, aos, soa, j_begin, cb_begin, sh, th, fl);
+  pairwise_tiled_kernel<D, TW, MINB, PAIRFN><<<grid, TW * 32, TiledSmem<D, TW>::BYTES, st>>>(g, aos, soa, j_begin, cb_begin, sh, th, fl);
 }
 
 void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, const double* soa, int j_begin, Shard sh,
@@ -213,13 +283,15 @@ void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, co
   dim3 grid((g.n + TILE_SEG - 1) / TILE_SEG, cb_end - cb_begin);
   if (dim == 3) {
     switch (g_tiled_variant) {
-      case 1: launch_variant<3, 10, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st); break;
-      case 3: launch_variant<3, 8, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st); break;
-      case 0: launch_variant<3, 4, 2>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st); break;
-      default: launch_variant<3, 12, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st); break;
+      case 1: launch_variant<3, 10, 1, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st); break;
+      case 3: launch_variant<3, 8, 1, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st); break;
+      case 0: launch_variant<3, 4, 2, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st); break;
+      case 2: launch_variant<3, 12, 1, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st); break;
+      default: launch_variant<3, 12, 1, 2>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st); break;
     }
   } else {
-    launch_variant<2, 12, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st);
+    if (g_tiled_variant == 2) launch_variant<2, 12, 1, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st);
+    else launch_variant<2, 12, 1, 2>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st);
   }
 }
 

@@ -2,6 +2,7 @@
 // CPU test-suite can prove, without a GPU, that its block-structured arithmetic is bit-identical to the
 // dense oracle.  Built by tests/test_cpu_math_parity.py with g++ -ffp-contract=off.
 #include "rpgo_math.cuh"
+#include "rpgo_pair_v2.cuh"
 
 using namespace rpgo;
 
@@ -51,6 +52,19 @@ static int pair_v1_t(const double* Ta, const double* Tb, const double* lci, cons
   return ok;
 }
 
+template <int D>
+static int pair_v2_t(const double* Ta, const double* Tb, const double* lci, const double* Tc, const double* Td,
+                     const double* lcj, const double* thr, double* dist, int* bad) {
+  Thresholds th;
+  th.odom = thr[0]; th.lc = thr[1]; th.odom_trans = thr[2]; th.odom_rot = thr[3]; th.dist_trans = thr[4];
+  th.dist_rot = thr[5]; th.band = 1e-9;
+  bool nr, bd;
+  double scr[64];
+  const bool ok = pair_check_v2<D>(Ta, 1, Tb, 1, lci, 1, Tc, 1, Td, 1, lcj, 1, scr, 1, th, dist, &nr, &bd);
+  *bad = bd;
+  return ok;
+}
+
 #define DISPATCH(d, m, F, ...)                                   \
   ((d) == 3 ? ((m) == 0 ? F<3, 0>(__VA_ARGS__) : F<3, 1>(__VA_ARGS__)) \
             : ((m) == 0 ? F<2, 0>(__VA_ARGS__) : F<2, 1>(__VA_ARGS__)))
@@ -75,6 +89,10 @@ int shim_pair_check(int d, int mode, const double* Ta, const double* Tb, const d
 int shim_pair_check_v1(int d, const double* Ta, const double* Tb, const double* lci, const double* Tc,
                        const double* Td, const double* lcj, const double* thr, double* dist, int* near) {
   return d == 3 ? pair_v1_t<3>(Ta, Tb, lci, Tc, Td, lcj, thr, dist, near) : pair_v1_t<2>(Ta, Tb, lci, Tc, Td, lcj, thr, dist, near);
+}
+int shim_pair_check_v2(int d, const double* Ta, const double* Tb, const double* lci, const double* Tc,
+                       const double* Td, const double* lcj, const double* thr, double* dist, int* bad) {
+  return d == 3 ? pair_v2_t<3>(Ta, Tb, lci, Tc, Td, lcj, thr, dist, bad) : pair_v2_t<2>(Ta, Tb, lci, Tc, Td, lcj, thr, dist, bad);
 }
 void shim_compose(int d, int mode, const double* a, const double* b, double* o) { DISPATCH(d, mode, compose_t, a, b, o); }
 void shim_between(int d, int mode, const double* a, const double* b, double* o) { DISPATCH(d, mode, between_t, a, b, o); }

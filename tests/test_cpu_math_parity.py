@@ -27,6 +27,7 @@ def shim():
     L.shim_entry_size.restype = C.c_int
     L.shim_pair_check.restype = C.c_int
     L.shim_pair_check_v1.restype = C.c_int
+    L.shim_pair_check_v2.restype = C.c_int
     return L
 
 
@@ -82,6 +83,7 @@ def test_pair_check_pcm_bitwise(shim, d):
     rng = np.random.default_rng(200 + d)
     n = orc.ndim(d)
     thr = np.array([1.0, 3.0, 1, 1, 1, 1.0])
+    n_bad = [0]
     for t in range(400):
         P = [rand_pose(rng, d, 3.0) for _ in range(6)]
         Ccum = [rand_cov(rng, n, 0.02) for _ in range(2)]
@@ -107,6 +109,15 @@ def test_pair_check_pcm_bitwise(shim, d):
         ok1 = shim.shim_pair_check_v1(d, *[dp(e) for e in E], dp(thr), C.byref(d1), C.byref(near))
         assert (d1.value == want) or (np.isnan(d1.value) and np.isnan(want)), ("v1", t, d1.value, want)
         assert bool(ok1) == bool(ok)
+        # straight-line form: either it flags the lane for the exact path, or it agrees bit for bit
+        d2 = C.c_double(); bad = C.c_int()
+        ok2 = shim.shim_pair_check_v2(d, *[dp(e) for e in E], dp(thr), C.byref(d2), C.byref(bad))
+        if bad.value:
+            n_bad[0] += 1
+        else:
+            assert d2.value == want, ("v2", t, d2.value, want)
+            assert bool(ok2) == bool(ok)
+    assert n_bad[0] < 400  # random (non-trajectory) covariances are mostly indefinite differences: flagged, never wrong
 
 
 @pytest.mark.parametrize("d", [3, 2])
@@ -166,3 +177,35 @@ def test_div_by_equals_ieee_division(shim):
         a = np.ascontiguousarray(a); x = np.ascontiguousarray(x)
         total += shim.shim_div_by_mismatches(n, dp(a), dp(x))
     assert total == 0
+
+
+def test_pair_check_v2_on_trajectory_data(shim):
+    """On realistic inputs (a synthetic helix graph) the straight-line form must agree bit for bit with the oracle's
+    pairwise distances and flag (almost) nothing for the exact path."""
+    import importlib
+    import sys
+    sys.path.insert(0, ROOT)
+    synth = importlib.import_module("kimera-rpgo_b200.synth")
+    gph = synth.config2(seed=3, P=500, n=60, outlier_frac=0.4)
+    o = orc.OraclePcm(3, 0, odom_threshold=-1, lc_threshold=5.0)
+    o.update(gph["odom"], gph["values"])
+    o.update(gph["lcs"], [])
+    _, dist = o.group_adj(0)
+    thr = np.array([1.0, 5.0, 1, 1, 1, 1.0])
+    ent = []
+    for f in gph["lcs"]:
+        pf, cf, _, rf = o.traj_get(f[1])
+        pb, cb, _, rb = o.traj_get(f[2])
+        ent.append((entry(shim, 3, pf, cf, rf), entry(shim, 3, pb, cb, rb), entry(shim, 3, f[3], f[4], 1)))
+    n_bad = 0
+    n = len(ent)
+    for i in range(n):
+        for j in range(i + 1, n):
+            d2 = C.c_double(); bad = C.c_int()
+            shim.shim_pair_check_v2(3, dp(ent[i][0]), dp(ent[i][1]), dp(ent[i][2]), dp(ent[j][0]), dp(ent[j][1]), dp(ent[j][2]),
+                                    dp(thr), C.byref(d2), C.byref(bad))
+            if bad.value:
+                n_bad += 1
+            else:
+                assert d2.value == dist[i, j], (i, j, d2.value, dist[i, j])
+    assert n_bad <= 0.02 * n * (n - 1) / 2, n_bad

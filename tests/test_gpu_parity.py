@@ -362,3 +362,28 @@ def test_single_closure_and_disabled_checks():
         calls = [(gph["odom"], gph["values"])] + [([lc], []) for lc in gph["lcs"]]
         o, g = run_both(3, 0, params, calls)
         assert o.num_inliers() == g.num_inliers()
+
+
+def test_straight_line_operations_equal_ieee():
+    """10^9 random operand pairs: the branch-free rcp / div / sqrt sequences == the built-in IEEE operations
+    whenever they do not flag the operand for the exact path."""
+    import ctypes as C
+    lib = pkg._capi.load()
+    m, c = C.c_uint64(), C.c_uint64()
+    assert lib.rpgo_debug_check_fastmath(1_000_000_000, 12345, C.byref(m), C.byref(c)) == 0
+    assert c.value > 2_000_000_000 and m.value == 0, (m.value, c.value)
+
+
+def test_straight_line_kernel_equals_direct_kernel():
+    """kernel variant 24 (pair_check_v2: straight-line + exact fallback) against the plain direct kernel."""
+    n = 12000
+    arr = synth.as_arrays(synth.config2(seed=8, P=n, n=n))
+    bits = []
+    for kern in (pkg.KERNEL_DIRECT, 24, 22):
+        g = PcmGpu(3, 0, kernel=kern, odom_threshold=-1, lc_threshold=5.0)
+        g.odom_append_arrays(arr["o_prev"], arr["o_new"], arr["o_pose"], arr["o_cov"], arr["o_init"])
+        g.lc_append_arrays(arr["l_from"], arr["l_to"], arr["l_pose"], arr["l_cov"])
+        bits.append((g.group_bits(0), g.flagged(0)[0]))
+        g.close()
+    assert np.array_equal(bits[0][0], bits[1][0]) and bits[0][1] == bits[1][1]
+    assert np.array_equal(bits[0][0], bits[2][0]) and bits[0][1] == bits[2][1]
