@@ -112,6 +112,17 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
                    const double* pose, const double* cov, uint8_t* accepted, int32_t* group, int32_t* index,
                    double* odom_dist);
 
+/* ---- N3: landmark observations (Pcm.h:207-220 first observation; :437-455 + incrementLandmarkAdjMatrix
+ * :775-844 re-observations) -----------------------------------------------------------------------------
+ * Appends n observations pose_key[i] -> landmark_key (measured pose / covariance as in rpgo_lc_append) to the
+ * landmark's own group and extends its adjacency: observations (i -> l), (j -> l) are consistent iff
+ * (getBetween(i, j) . j_pose_l)^-1 . i_pose_l passes the loop-consistency check (getBetween's different-prefix
+ * path included, as the reference runs it).  reset != 0 empties the group first: a FIRST_LANDMARK_OBSERVATION
+ * replaces landmarks_[key] (Pcm.h:218).  *group_out is an ordinal for rpgo_find_inliers / rpgo_adj_bits /
+ * rpgo_group_info (which reports id1 = id2 = chr(landmark_key)). */
+int rpgo_landmark_append(rpgo_handle* h, uint64_t landmark_key, int64_t n, const uint64_t* pose_key, const double* pose,
+                         const double* cov, int32_t reset, int32_t* group_out);
+
 int32_t rpgo_num_groups(rpgo_handle* h);
 /* prefixes (id1 <= id2) and number of stored closures of group g */
 int rpgo_group_info(rpgo_handle* h, int32_t g, uint8_t* id1, uint8_t* id2, int64_t* n);

@@ -37,6 +37,7 @@ SYMBOLS = [
     ("rpgo_traj_get", C.c_int, [C.c_void_p, C.c_uint64, c_dp, c_dp, c_i32p, c_i32p]),
     ("rpgo_traj_size", C.c_int64, [C.c_void_p]),
     ("rpgo_lc_append", C.c_int, [C.c_void_p, C.c_int64, c_u64p, c_u64p, c_dp, c_dp, c_u8p, c_i32p, c_i32p, c_dp]),
+    ("rpgo_landmark_append", C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, c_u64p, c_dp, c_dp, C.c_int32, c_i32p]),
     ("rpgo_num_groups", C.c_int32, [C.c_void_p]),
     ("rpgo_group_info", C.c_int, [C.c_void_p, C.c_int32, c_u8p, c_u8p, c_i64p]),
     ("rpgo_find_group", C.c_int32, [C.c_void_p, C.c_uint8, C.c_uint8]),

@@ -108,12 +108,16 @@ struct Group {
   int64_t stride32 = 0;  /* adjacency row stride in 32-bit words (= cap / 32) */
   DevBuf lc, idxf, idxb, pfx, bits, deg, fl_pairs, fl_count;
   DevBuf rec_aos, rec_soa; /* gathered per-closure records for the tiled kernel */
+  bool landmark = false;   /* N3: observations of one landmark instead of closures of one prefix pair */
+  uint64_t lkey = 0;
+  DevBuf idxa0;
+  std::vector<int32_t> h_idxa0;
   int64_t gathered = 0;    /* closures [0, gathered) have up-to-date records */
   std::vector<uint64_t> kfrom, kto;
   std::vector<int32_t> h_idxf, h_idxb;
   std::vector<uint8_t> h_pfx;
   explicit Group(Arena* a) {
-    for (DevBuf* b : {&lc, &idxf, &idxb, &pfx, &bits, &deg, &fl_pairs, &fl_count, &rec_aos, &rec_soa}) b->arena = a;
+    for (DevBuf* b : {&lc, &idxf, &idxb, &pfx, &bits, &deg, &fl_pairs, &fl_count, &rec_aos, &rec_soa, &idxa0}) b->arena = a;
   }
 };
 
@@ -146,6 +150,7 @@ struct rpgo_handle {
 
   std::vector<Group*> groups;
   std::map<std::pair<uint8_t, uint8_t>, int32_t> gindex;
+  std::map<uint64_t, int32_t> lindex; /* landmark key -> group ordinal */
 
   /* staging (the pinned host buffer is per thread, shared by successive handles: cudaMallocHost is slow) */
   DevBuf d_stage;
@@ -199,6 +204,7 @@ static GroupView group_view(rpgo_handle* h, Group* g) {
   v.stride32 = g->stride32;
   v.deg = g->deg.as<int32_t>();
   v.n = (int32_t)g->n;
+  v.idx_a0 = g->idxa0.as<int32_t>();
   return v;
 }
 
@@ -223,12 +229,13 @@ static int ensure_group(rpgo_handle* h, Group* g, int64_t need) {
   H_CHECK_CUDA(h, g->idxb.ensure((size_t)ncap * 4, (size_t)g->n * 4, st));
   H_CHECK_CUDA(h, g->pfx.ensure((size_t)ncap, (size_t)g->n, st));
   H_CHECK_CUDA(h, g->deg.ensure((size_t)ncap * 4, 0, st));
-  if (h->loop_check && h->mode == MODE_PCM) {
+  if (g->landmark) H_CHECK_CUDA(h, g->idxa0.ensure((size_t)ncap * 4, (size_t)g->n * 4, st));
+  if (h->loop_check && h->mode == MODE_PCM && !g->landmark) {
     const size_t rn = (size_t)tiled_record_doubles(h->dim) * 8;
     H_CHECK_CUDA(h, g->rec_aos.ensure((size_t)ncap * rn + 256, (size_t)g->n * rn, st));
     H_CHECK_CUDA(h, g->rec_soa.ensure((size_t)ncap * rn + 256, (size_t)((g->n + 31) / 32) * 32 * rn, st));
   }
-  if (h->loop_check) {
+  if (h->loop_check || g->landmark) {
     /* adjacency: ncap rows x ncap/32 words; the row pitch changes, so copy row by row (2D copy) */
     const int64_t nstride = ncap / 32;
     /* in multi-GPU mode rows are padded to 2*world chunks */
@@ -263,6 +270,12 @@ static Flagged group_flagged(Group* g) {
 static int run_pairwise(rpgo_handle* h, Group* g, int64_t j_begin, double* dist_dev) {
   if (!h->loop_check || g->n < 2) return RPGO_OK;
   GroupView v = group_view(h, g);
+  if (g->landmark) {
+    launch_landmark_direct(h->dim, h->mode, v, h->traj.as<double>(), (int)j_begin, h->th, group_flagged(g), dist_dev, h->stream);
+    h->launches += 1;
+    H_CHECK_CUDA(h, cudaGetLastError());
+    return RPGO_OK;
+  }
   Shard sh = group_shard(h, g);
   int kernel = h->cfg.kernel;
   {
@@ -294,7 +307,7 @@ static int run_pairwise(rpgo_handle* h, Group* g, int64_t j_begin, double* dist_
 }
 
 static int finalize_group(rpgo_handle* h, Group* g, int64_t j_begin) {
-  if (!h->loop_check || g->n < 1) return RPGO_OK;
+  if ((!h->loop_check && !g->landmark) || g->n < 1) return RPGO_OK;
   launch_mirror(g->bits.as<uint32_t>(), g->stride32, (int)g->n, (int)j_begin, h->stream);
   launch_degree(g->bits.as<uint32_t>(), g->stride32, (int)g->n, g->deg.as<int32_t>(), h->stream);
   h->launches += 2;
@@ -606,7 +619,10 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
       for (int64_t k = 0; k < g->n; ++k) {
         g->h_idxf[k] = traj_lookup(h, g->kfrom[k]);
         g->h_idxb[k] = traj_lookup(h, g->kto[k]);
+        if (g->landmark) g->h_idxa0[k] = traj_lookup(h, (uint64_t)key_chr(g->kfrom[k]) << 56);
       }
+      if (g->landmark && g->n > 0 && g->idxa0.p)
+        H_CHECK_CUDA(h, cudaMemcpyAsync(g->idxa0.p, g->h_idxa0.data(), (size_t)g->n * 4, cudaMemcpyHostToDevice, st));
       if (g->n > 0 && g->idxf.p) {
         H_CHECK_CUDA(h, cudaMemcpyAsync(g->idxf.p, g->h_idxf.data(), (size_t)g->n * 4, cudaMemcpyHostToDevice, st));
         H_CHECK_CUDA(h, cudaMemcpyAsync(g->idxb.p, g->h_idxb.data(), (size_t)g->n * 4, cudaMemcpyHostToDevice, st));
@@ -752,6 +768,107 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
   return RPGO_OK;
 }
 
+int rpgo_landmark_append(rpgo_handle* h, uint64_t landmark_key, int64_t n, const uint64_t* pose_key, const double* pose,
+                         const double* cov, int32_t reset, int32_t* group_out) {
+  if (!h || n < 0) return RPGO_ERR_INVALID;
+  if (n > 0 && (!pose_key || !pose || !cov)) return RPGO_ERR_INVALID;
+  const int E = h->E, PS = h->PS, NN = h->NN;
+  cudaStream_t st = h->stream;
+  int32_t gi;
+  auto it = h->lindex.find(landmark_key);
+  if (it == h->lindex.end()) {
+    Group* g = new Group(&h->arena);
+    g->landmark = true;
+    g->lkey = landmark_key;
+    g->id1 = g->id2 = key_chr(landmark_key);
+    gi = (int32_t)h->groups.size();
+    h->groups.push_back(g);
+    h->lindex[landmark_key] = gi;
+  } else {
+    gi = it->second;
+  }
+  if (group_out) *group_out = gi;
+  Group* g = h->groups[gi];
+  if (reset && g->n > 0) {
+    if (g->bits.p) H_CHECK_CUDA(h, cudaMemsetAsync(g->bits.p, 0, g->bits.cap, st));
+    if (g->fl_count.p) H_CHECK_CUDA(h, cudaMemsetAsync(g->fl_count.p, 0, 8, st));
+    g->n = 0;
+    g->kfrom.clear(); g->kto.clear(); g->h_idxf.clear(); g->h_idxb.clear(); g->h_pfx.clear(); g->h_idxa0.clear();
+  }
+  if (n == 0) return RPGO_OK;
+  if (h->traj_dirty) {
+    /* same late-odometry rule as rpgo_lc_append: stored observations must see entries that appeared since */
+    for (Group* q : h->groups) {
+      for (int64_t k = 0; k < q->n; ++k) {
+        q->h_idxf[k] = traj_lookup(h, q->kfrom[k]);
+        q->h_idxb[k] = traj_lookup(h, q->kto[k]);
+        if (q->landmark) q->h_idxa0[k] = traj_lookup(h, (uint64_t)key_chr(q->kfrom[k]) << 56);
+      }
+      if (q->n > 0 && q->idxf.p) {
+        H_CHECK_CUDA(h, cudaMemcpyAsync(q->idxf.p, q->h_idxf.data(), (size_t)q->n * 4, cudaMemcpyHostToDevice, st));
+        H_CHECK_CUDA(h, cudaMemcpyAsync(q->idxb.p, q->h_idxb.data(), (size_t)q->n * 4, cudaMemcpyHostToDevice, st));
+        if (q->landmark && q->idxa0.p)
+          H_CHECK_CUDA(h, cudaMemcpyAsync(q->idxa0.p, q->h_idxa0.data(), (size_t)q->n * 4, cudaMemcpyHostToDevice, st));
+      }
+      q->gathered = 0;
+    }
+    H_CHECK_CUDA(h, cudaStreamSynchronize(st));
+    h->traj_dirty = false;
+  }
+  const int64_t o = g->n;
+  int rc = ensure_group(h, g, o + n);
+  if (rc != RPGO_OK) return rc;
+  /* stage raw pose | cov, run the factor constructor (no odometry check), scatter into the group */
+  const size_t o_cov = (size_t)n * PS * 8, o_if = o_cov + (size_t)n * NN * 8, o_ck = o_if + (size_t)n * 4,
+               o_dst = (o_ck + (size_t)n + 15) & ~size_t(15), total = o_dst + (size_t)n * 8;
+  char* pin = (char*)pinned_staging().ensure(total + 64);
+  if (!pin) { h->err = "pinned staging allocation failed"; return RPGO_ERR_NOMEM; }
+  memcpy(pin, pose, (size_t)n * PS * 8);
+  memcpy(pin + o_cov, cov, (size_t)n * NN * 8);
+  int32_t* p_if = (int32_t*)(pin + o_if);
+  uint8_t* p_ck = (uint8_t*)(pin + o_ck);
+  uint64_t* p_dst = (uint64_t*)(pin + o_dst);
+  for (int64_t k = 0; k < n; ++k) {
+    const uint8_t c = key_chr(pose_key[k]);
+    const int32_t idx = traj_lookup(h, pose_key[k]);
+    const uint64_t a0 = (uint64_t)c << 56;
+    p_if[k] = idx;
+    p_ck[k] = 0;
+    if (idx == 0 && !h->key2idx.count(pose_key[k])) h->missing_refs.insert(pose_key[k]);
+    if (!h->key2idx.count(a0)) h->missing_refs.insert(a0);
+    h->prefixes.insert(c); /* odom_trajectories_[chr] is created by the lookup (Pcm.h:823-824) */
+    g->kfrom.push_back(pose_key[k]);
+    g->kto.push_back(landmark_key);
+    g->h_idxf.push_back(idx);
+    g->h_idxb.push_back(0);
+    g->h_pfx.push_back(c);
+    g->h_idxa0.push_back(traj_lookup(h, a0));
+    p_dst[k] = (uint64_t)(uintptr_t)(g->lc.as<double>() + (size_t)(o + k) * E);
+  }
+  H_CHECK_CUDA(h, h->d_stage.ensure(total, 0, st));
+  H_CHECK_CUDA(h, h->d_lcent.ensure((size_t)n * E * 8, 0, st));
+  H_CHECK_CUDA(h, h->d_ok.ensure((size_t)n, 0, st));
+  H_CHECK_CUDA(h, h->d_dist.ensure((size_t)n * 8, 0, st));
+  H_CHECK_CUDA(h, cudaMemcpyAsync(h->d_stage.p, pin, total, cudaMemcpyHostToDevice, st));
+  char* d = (char*)h->d_stage.p;
+  launch_lc_prepare(h->dim, h->mode, (int)n, (const double*)d, (const double*)(d + o_cov), (const int32_t*)(d + o_if),
+                    (const int32_t*)(d + o_if), (const uint8_t*)(d + o_ck), h->traj.as<double>(), h->th, h->d_lcent.as<double>(),
+                    h->d_ok.as<uint8_t>(), h->d_dist.as<double>(), st);
+  launch_scatter_entries(h->dim, (int)n, h->d_lcent.as<double>(), (const uint64_t*)(d + o_dst), st);
+  h->launches += 2;
+  g->n = o + n;
+  H_CHECK_CUDA(h, cudaMemcpyAsync(g->idxf.as<int32_t>() + o, g->h_idxf.data() + o, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  H_CHECK_CUDA(h, cudaMemcpyAsync(g->idxb.as<int32_t>() + o, g->h_idxb.data() + o, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  H_CHECK_CUDA(h, cudaMemcpyAsync(g->pfx.as<uint8_t>() + o, g->h_pfx.data() + o, (size_t)n, cudaMemcpyHostToDevice, st));
+  H_CHECK_CUDA(h, cudaMemcpyAsync(g->idxa0.as<int32_t>() + o, g->h_idxa0.data() + o, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  rc = run_pairwise(h, g, o, nullptr);
+  if (rc != RPGO_OK) return rc;
+  rc = finalize_group(h, g, o);
+  if (rc != RPGO_OK) return rc;
+  H_CHECK_CUDA(h, cudaStreamSynchronize(st));
+  return RPGO_OK;
+}
+
 int32_t rpgo_num_groups(rpgo_handle* h) { return h ? (int32_t)h->groups.size() : 0; }
 
 int rpgo_group_info(rpgo_handle* h, int32_t g, uint8_t* id1, uint8_t* id2, int64_t* n) {
@@ -771,7 +888,7 @@ int32_t rpgo_find_group(rpgo_handle* h, uint8_t id1, uint8_t id2) {
 int rpgo_lc_remove_last(rpgo_handle* h, int32_t gi, uint64_t* key_from, uint64_t* key_to) {
   if (!h || gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
   Group* g = h->groups[gi];
-  if (g->n <= 0) return RPGO_ERR_NOT_FOUND;
+  if (g->n <= 0 || g->landmark) return RPGO_ERR_NOT_FOUND; /* the reference never removes landmark observations */
   if (key_from) *key_from = g->kfrom.back();
   if (key_to) *key_to = g->kto.back();
   g->kfrom.pop_back();
@@ -797,7 +914,7 @@ int rpgo_find_inliers(rpgo_handle* h, int32_t gi, int32_t clique_mode, int64_t n
   if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
   Group* g = h->groups[gi];
   const int n = (int)g->n;
-  if (n <= 0 || !h->loop_check) { h->err = "find_inliers: empty group or loop check disabled"; return RPGO_ERR_INVALID; }
+  if (n <= 0 || (!h->loop_check && !g->landmark)) { h->err = "find_inliers: empty group or loop check disabled"; return RPGO_ERR_INVALID; }
   cudaStream_t st = h->stream;
   const int W = (n + 31) / 32;
   const int64_t blocks = 148 * 8;

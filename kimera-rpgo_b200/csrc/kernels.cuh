@@ -22,6 +22,7 @@ struct GroupView {
   const int32_t* idx_front;  /* trajectory entry index of key_from (0 = default/identity entry) */
   const int32_t* idx_back;   /* trajectory entry index of key_to */
   const uint8_t* pfx_front;  /* Symbol::chr() of key_from (decides the Pcm.h:691-698 key swap) */
+  const int32_t* idx_a0;     /* landmark groups: trajectory entry of Symbol(chr(pose key), 0); else nullptr */
   uint32_t* bits;            /* adjacency bitset, row stride stride32 32-bit words */
   int64_t stride32;
   int32_t* deg;
@@ -61,6 +62,9 @@ int tiled_record_doubles(int dim);
 void launch_gather_records(int dim, GroupView g, const double* traj, int k0, double* aos, double* soa, cudaStream_t st);
 void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, const double* soa, int j_begin, Shard sh,
                            Thresholds th, Flagged fl, cudaStream_t st);
+/* N3: landmark re-observation matrix (one thread per pair of observations of the same landmark) */
+void launch_landmark_direct(int dim, int mode, GroupView g, const double* traj, int j_begin, Thresholds th, Flagged fl,
+                            double* dist_out, cudaStream_t st);
 /* bitset maintenance */
 void launch_mirror(uint32_t* bits, int64_t stride32, int n, int j_begin, cudaStream_t st);
 void launch_degree(const uint32_t* bits, int64_t stride32, int n, int32_t* deg, cudaStream_t st);

@@ -421,6 +421,62 @@ void launch_pairwise_direct(int dim, int mode, GroupView g, const double* traj, 
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * N3: landmark re-observations.  Same tiling as the direct pairwise kernel: warp = older observation i x 32
+ * newer observations j, decisions ballot-packed into word (i, j/32).  Groups are tiny (a handful of
+ * observations per landmark), so this is latency- not throughput-relevant.
+ * ---------------------------------------------------------------------------------------------- */
+template <int D, int MODE>
+__global__ void __launch_bounds__(128) landmark_direct_kernel(GroupView g, const double* __restrict__ traj, int j_begin,
+                                                              int w_begin, Thresholds th, Flagged fl, double* dist_out) {
+  constexpr int E = Dim<D>::ENTRY;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int w = w_begin + blockIdx.x;
+  const int i = blockIdx.y * (blockDim.x >> 5) + wib;
+  const int j = w * 32 + lane;
+  if (i >= g.n || i >= w * 32 + 31) return;
+  bool ok = false;
+  if (j < g.n && j > i && j >= j_begin) {
+    const bool cross = g.pfx_front[i] != g.pfx_front[j];
+    double dist;
+    bool near;
+    ok = landmark_pair_check<D, MODE>(traj + (size_t)g.idx_front[i] * E, traj + (size_t)g.idx_front[j] * E,
+                                      traj + (size_t)g.idx_a0[i] * E, traj, cross, g.lc + (size_t)i * E, g.lc + (size_t)j * E, th,
+                                      &dist, &near);
+    if (near) {
+      const unsigned long long slot = atomicAdd(fl.count, 1ULL);
+      if ((int64_t)slot < fl.cap) {
+        fl.pairs[2 * slot] = i;
+        fl.pairs[2 * slot + 1] = j;
+      }
+    }
+    if (dist_out) {
+      dist_out[(size_t)i * g.n + j] = dist;
+      dist_out[(size_t)j * g.n + i] = dist;
+    }
+  }
+  const unsigned word = __ballot_sync(0xffffffffu, ok);
+  if (lane == 0) {
+    unsigned keep = 0;
+    if (j_begin > w * 32) keep = (j_begin >= w * 32 + 32) ? 0xffffffffu : ((1u << (j_begin - w * 32)) - 1u);
+    uint32_t* p = g.bits + (size_t)i * g.stride32 + w;
+    *p = (*p & keep) | word;
+  }
+}
+
+void launch_landmark_direct(int dim, int mode, GroupView g, const double* traj, int j_begin, Thresholds th, Flagged fl,
+                            double* dist_out, cudaStream_t st) {
+  if (g.n < 2 || j_begin >= g.n) return;
+  const int w_begin = j_begin / 32;
+  const int w_end = (g.n + 31) / 32;
+  const int warps = 4;
+  dim3 grid(w_end - w_begin, (g.n + warps - 1) / warps);
+#define CALL(D, M) landmark_direct_kernel<D, M><<<grid, warps * 32, 0, st>>>(g, traj, j_begin, w_begin, th, fl, dist_out)
+  RPGO_DISPATCH(dim, mode, CALL);
+#undef CALL
+}
+
+/* ------------------------------------------------------------------------------------------------
  * mirror: fill row j (columns i < j) from column j of rows i < j, for rows j >= j_begin.
  * One warp transposes a 32x32 bit block with 32 ballots.
  * ---------------------------------------------------------------------------------------------- */

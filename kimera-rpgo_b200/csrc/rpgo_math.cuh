@@ -827,6 +827,40 @@ RPGO_FN bool pair_check(const double* Ta, int sa, const double* Tb, int sb, cons
 }
 
 
+/* Landmark re-observation check (incrementLandmarkAdjMatrix, Pcm.h:810-832): observations (i -> l) and (j -> l)
+ *   i_odom_j = Trajectory::getBetween(key_i, key_j);  loop = (i_odom_j . j_pose_l)^-1 . i_pose_l
+ * `cross` selects getBetween's different-prefix path (GraphUtils.h:43-57) exactly as the reference runs it: inside
+ * robot i's Trajectory the foreign keys do not exist, so operator[] yields default entries (E0) for them. */
+template <int D, int MODE>
+RPGO_FN bool landmark_pair_check(const double* Ei, const double* Ej, const double* Ea0, const double* E0, bool cross,
+                                 const double* lci, const double* lcj, const Thresholds& th, double* dist, bool* near) {
+  typedef PoseT<D, MODE> PT;
+  PT x, y, z;
+  if (!cross) {
+    PT ei, ej;
+    load_entry<D, MODE>(Ei, 1, ei);
+    load_entry<D, MODE>(Ej, 1, ej);
+    pt_between<D, MODE>(ei, ej, x);
+  } else {
+    PT ea0, ei, e0, pa, pb, pab, r;
+    load_entry<D, MODE>(Ea0, 1, ea0);
+    load_entry<D, MODE>(Ei, 1, ei);
+    load_entry<D, MODE>(E0, 1, e0);
+    pt_between<D, MODE>(ea0, ei, pa);  /* pose_a   = poses[a0].between(poses[key_a]) */
+    pt_between<D, MODE>(e0, e0, pb);   /* pose_b   = poses[b0].between(poses[key_b]) : both default entries */
+    pt_between<D, MODE>(ea0, e0, pab); /* pose_a0b0 = poses[a0].between(poses[b0]) */
+    pt_inverse_inplace<D, MODE>(pa);
+    pt_compose<D, MODE>(pa, pab, r);
+    pt_compose<D, MODE>(r, pb, x);
+  }
+  load_entry<D, MODE>(lcj, 1, y);
+  pt_compose<D, MODE>(x, y, z); /* i_path_l */
+  pt_inverse_inplace<D, MODE>(z);
+  load_entry<D, MODE>(lci, 1, y);
+  pt_compose<D, MODE>(z, y, x); /* loop */
+  return check_consistent<D, MODE>(x, th, false, dist, near);
+}
+
 /* ------------------------------------------------------------------------------------------------
  * pair_check_v1: same arithmetic as pair_check (bit-identical results), restructured for the tiled
  * kernel:

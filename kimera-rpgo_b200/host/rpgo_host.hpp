@@ -251,13 +251,25 @@ class PcmGpu : public OutlierRemovalT<P> {
         do_optimize = true;
         continue;
       }
-      if (isSpecialSymbol(gtsam_lite::Symbol(b->k1).chr()) || isSpecialSymbol(gtsam_lite::Symbol(b->k2).chr()))
-        throw std::runtime_error("landmark factors are not handled by the GPU path yet (SURVEY 8(f) N3)");
+      if (isSpecialSymbol(gtsam_lite::Symbol(b->k1).chr()) || isSpecialSymbol(gtsam_lite::Symbol(b->k2).chr())) {
+        // landmark observation, Pcm.h:180-188
+        if (new_values.exists(b->k1) || new_values.exists(b->k2)) landmarkFirst(b);   // FIRST_LANDMARK_OBSERVATION :207-220
+        else if (b->k1 != b->k2) lcs.push_back(b);                                    // re-observation
+        continue;
+      }
       if (b->k1 + 1 == b->k2 && new_values.exists(b->k2)) odom.push_back(b);   // ODOMETRY, Pcm.h:189-191
       else if (b->k1 != b->k2) lcs.push_back(b);                                // LOOP_CLOSURE, Pcm.h:221-228
     }
     if (!odom.empty()) appendOdom(odom, *output_values);
     if (!lcs.empty()) {
+      std::vector<std::shared_ptr<Between>> plain;
+      for (auto& f : lcs) {
+        if (isSpecialSymbol(gtsam_lite::Symbol(f->k1).chr()) || isSpecialSymbol(gtsam_lite::Symbol(f->k2).chr()))
+          landmarkReobserve(f, *output_values);                                       // Pcm.h:437-455
+        else
+          plain.push_back(f);
+      }
+      lcs.swap(plain);
       std::map<int, size_t> num_new = appendLoopClosures(lcs, *output_values);
       if (params_.incremental) findInliersIncremental(num_new); else findInliers();
       do_optimize = true;
@@ -306,6 +318,7 @@ class PcmGpu : public OutlierRemovalT<P> {
     Graph factors, consistent_factors;
     std::vector<int> inlier_idx;
     char id1 = 0, id2 = 0;
+    bool is_landmark = false;
   };
 
   bool isSpecialSymbol(unsigned char c) const {
@@ -365,6 +378,34 @@ class PcmGpu : public OutlierRemovalT<P> {
     return num_new;
   }
 
+  // ---- landmarks: one group per landmark key (Pcm.h:109) ---------------------------------------------
+  Key landmarkKey(const Between& f) const { return isSpecialSymbol(gtsam_lite::Symbol(f.k1).chr()) ? f.k1 : f.k2; }
+  int landmarkAppend(const std::shared_ptr<Between>& f, bool reset) {
+    const Key lkey = landmarkKey(*f);
+    if (f->k1 == lkey) throw std::runtime_error("landmark observations must be stated pose -> landmark (Pcm.h:803-808)");
+    int32_t g = -1;
+    const uint64_t pk = f->k1;
+    check(rpgo_landmark_append(h_, lkey, 1, &pk, f->measured.m.data(), f->covariance.data(), reset ? 1 : 0, &g), "rpgo_landmark_append");
+    if (g >= (int)groups_.size()) groups_.resize(g + 1);
+    if (landmark_group_.find(lkey) == landmark_group_.end()) { landmark_group_[lkey] = g; landmark_order_.push_back(lkey); }
+    groups_[g].is_landmark = true;
+    return g;
+  }
+  void landmarkFirst(const std::shared_ptr<Between>& f) {
+    const int g = landmarkAppend(f, true);
+    groups_[g].factors = Graph();
+    groups_[g].factors.add(std::static_pointer_cast<gtsam_lite::Factor>(f));
+    groups_[g].consistent_factors = groups_[g].factors;
+    ++total_lc_;
+  }
+  void landmarkReobserve(const std::shared_ptr<Between>& f, const Values& vals) {
+    if (!vals.exists(f->k1) || !vals.exists(f->k2)) return;                           // Pcm.h:431-435
+    if (f->k1 == landmarkKey(*f)) return;
+    const int g = landmarkAppend(f, false);
+    groups_[g].factors.add(std::static_pointer_cast<gtsam_lite::Factor>(f));
+    ++total_lc_;
+  }
+
   void selectInliers(int g, int mode, int64_t n_new, int64_t prev, bool keep_if_zero) {
     Group& m = groups_[g];
     std::vector<int32_t> ids(std::max<size_t>(m.factors.size(), 1));
@@ -380,7 +421,7 @@ class PcmGpu : public OutlierRemovalT<P> {
     for (size_t g = 0; g < groups_.size(); ++g) {
       Group& m = groups_[g];
       if (m.factors.size() == 0) { m.consistent_factors = Graph(); continue; }
-      if (loop_check_) selectInliers((int)g, RPGO_CLIQUE_HEU, 0, 0, false);
+      if (loop_check_ || m.is_landmark) selectInliers((int)g, RPGO_CLIQUE_HEU, 0, 0, false);   // landmarks: Pcm.h:878-895
       else m.consistent_factors = m.factors;
       total_good_lc_ += m.consistent_factors.size();
     }
@@ -388,6 +429,8 @@ class PcmGpu : public OutlierRemovalT<P> {
   void findInliersIncremental(const std::map<int, size_t>& num_new) {                // Pcm.h:906-947
     for (auto& kv : num_new)
       selectInliers(kv.first, RPGO_CLIQUE_HEU_INCREMENTAL, (int64_t)kv.second, (int64_t)groups_[kv.first].consistent_factors.size(), true);
+    for (size_t g = 0; g < groups_.size(); ++g)
+      if (groups_[g].is_landmark && groups_[g].factors.size() > 0) selectInliers((int)g, RPGO_CLIQUE_HEU, 0, 0, false);   // Pcm.h:950-966
     total_good_lc_ = 0;
     for (auto& m : groups_) total_good_lc_ += m.consistent_factors.size();
   }
@@ -406,10 +449,12 @@ class PcmGpu : public OutlierRemovalT<P> {
     out.add(nfg_odom_);
     out.add(nfg_special_);
     for (auto& m : groups_) {
+      if (m.is_landmark) continue;
       if (std::find(ignored_.begin(), ignored_.end(), m.id1) != ignored_.end()) continue;
       if (std::find(ignored_.begin(), ignored_.end(), m.id2) != ignored_.end()) continue;
       out.add(m.consistent_factors);
     }
+    for (Key lk : landmark_order_) out.add(groups_[landmark_group_.at(lk)].consistent_factors);   // Pcm.h:996-1002
     return out;
   }
 
@@ -419,6 +464,8 @@ class PcmGpu : public OutlierRemovalT<P> {
   bool loop_check_ = true;
   Graph nfg_odom_, nfg_special_;
   std::vector<Group> groups_;
+  std::map<Key, int> landmark_group_;
+  std::vector<Key> landmark_order_;
   std::vector<int> lc_in_order_;
   std::vector<char> ignored_;
   size_t total_lc_ = 0, total_good_lc_ = 0;

@@ -69,6 +69,8 @@ class PcmGpu:
         self.group_factors = {}        # group ordinal -> [factor ids]
         self.group_consistent = {}     # group ordinal -> [factor ids]
         self.group_order = []
+        self.landmark_group = {}       # landmark key -> group ordinal
+        self.landmark_order = []
         self.lc_in_order = []
         self.ignored = []
         self.total_lc = 0
@@ -108,8 +110,12 @@ class PcmGpu:
             ftype, k1, k2 = f[0], int(f[1]), int(f[2])
             if ftype == BETWEEN:
                 if key_chr(k1) in self.special_symbols or key_chr(k2) in self.special_symbols:
-                    raise NotImplementedError("landmark (special symbol) factors are SURVEY §8(f) N3: not built yet")
-                if k1 + 1 == k2 and k2 in new_keys:
+                    # landmark observation, Pcm.h:180-188
+                    if k1 in new_keys or k2 in new_keys:
+                        self._landmark_first(fid, k1, k2, f[3], f[4])            # FIRST_LANDMARK_OBSERVATION :207-220
+                    elif k1 != k2:
+                        lcs.append((fid, k1, k2, f[3], f[4]))                    # re-observation: a loop closure
+                elif k1 + 1 == k2 and k2 in new_keys:
                     odom.append((fid, k1, k2, f[3], f[4]))
                 elif k1 != k2:
                     lcs.append((fid, k1, k2, f[3], f[4]))
@@ -123,7 +129,12 @@ class PcmGpu:
         if odom:
             self._odom_append(odom)
         if lcs:
-            num_new = self._lc_append(lcs)
+            is_lm = [key_chr(l[1]) in self.special_symbols or key_chr(l[2]) in self.special_symbols for l in lcs]
+            lm = [l for l, m in zip(lcs, is_lm) if m]
+            if lm:
+                lcs = [l for l, m in zip(lcs, is_lm) if not m]
+                self._landmark_reobserve(lm)
+            num_new = self._lc_append(lcs) if lcs else {}
             if self.incremental:
                 self._find_inliers_incremental(num_new)
             else:
@@ -220,6 +231,66 @@ class PcmGpu:
                 parallel.allgather_adjacency(self, g, dev)
         return num_new, acc
 
+    # ---- landmarks (Pcm.h:207-220, :437-455, :775-844) -----------------------------------------
+    def _landmark_key(self, k1, k2):
+        return k1 if key_chr(k1) in self.special_symbols else k2
+
+    def _landmark_call(self, lkey, obs, reset):
+        n = len(obs)
+        pk = np.array([o[1] for o in obs], dtype=np.uint64)
+        pose = np.ascontiguousarray(np.stack([np.asarray(o[2], dtype=np.float64) for o in obs])).reshape(n, self.ps)
+        cov = np.ascontiguousarray(np.stack([np.asarray(o[3], dtype=np.float64).reshape(self.n * self.n) for o in obs]))
+        g = C.c_int32(-1)
+        self._check(self.lib.rpgo_landmark_append(self.h, int(lkey), n, pk.ctypes.data_as(_capi.c_u64p), _dp(pose), _dp(cov),
+                                                  int(reset), C.byref(g)), "rpgo_landmark_append")
+        return g.value
+
+    def _landmark_first(self, fid, k1, k2, pose, cov):
+        lkey = self._landmark_key(k1, k2)
+        if k1 == lkey:
+            # the reference stores it, then trips over it at the first re-observation (Pcm.h:803-808 returns
+            # before saving the grown matrices; the next growth copies a wrongly sized block)
+            raise RpgoError("landmark observations must be stated pose -> landmark")
+        g = self._landmark_call(lkey, [(fid, k1, pose, cov)], reset=True)
+        if lkey not in self.landmark_group:
+            self.landmark_order.append(lkey)
+        self.landmark_group[lkey] = g
+        self.group_factors[g] = [fid]
+        self.group_consistent[g] = [fid]
+        self.total_lc += 1
+
+    def _landmark_reobserve(self, lm):
+        by_key = {}
+        for fid, k1, k2, pose, cov in lm:
+            if k1 not in self.values or k2 not in self.values:
+                continue                                           # Pcm.h:431-435
+            lkey = self._landmark_key(k1, k2)
+            if k1 == lkey:
+                continue                                           # malformed: see _landmark_first
+            by_key.setdefault(lkey, []).append((fid, k1, pose, cov))
+        for lkey, obs in by_key.items():
+            g = self._landmark_call(lkey, obs, reset=False)
+            if lkey not in self.landmark_group:
+                self.landmark_order.append(lkey)
+                self.landmark_group[lkey] = g
+                self.group_factors[g] = []
+                self.group_consistent[g] = []
+            self.group_factors[g].extend(o[0] for o in obs)
+            self.total_lc += len(obs)
+
+    def _landmark_inliers(self):  # Pcm.h:878-895
+        for lkey in self.landmark_order:
+            g = self.landmark_group[lkey]
+            fs = self.group_factors[g]
+            k, ids, _ = self.find_inliers_raw(g, CLIQUE_HEU)
+            self.group_consistent[g] = [fs[i] for i in ids[:k]]
+            self.total_good_lc += k
+
+    def landmarks(self):
+        """[(key, n_observations, n_inliers)] in first-seen order"""
+        return [(k, len(self.group_factors[self.landmark_group[k]]), len(self.group_consistent[self.landmark_group[k]]))
+                for k in self.landmark_order]
+
     def find_inliers_raw(self, g, clique_mode=CLIQUE_HEU, n_new=0, prev_size=0):
         """(size, ids, true_clique) straight from rpgo_find_inliers."""
         n = len(self.group_factors[g])
@@ -244,6 +315,7 @@ class PcmGpu:
             else:
                 self.group_consistent[g] = list(fs)
             self.total_good_lc += len(self.group_consistent[g])
+        self._landmark_inliers()
 
     def _find_inliers_incremental(self, num_new):  # Pcm.h:906-970
         for g, nn in num_new.items():
@@ -252,7 +324,8 @@ class PcmGpu:
             k, ids, _ = self.find_inliers_raw(g, CLIQUE_HEU_INCREMENTAL, nn, prev)
             if k > 0:
                 self.group_consistent[g] = [fs[i] for i in ids[:k]]
-        self.total_good_lc = sum(len(v) for v in self.group_consistent.values())
+        self.total_good_lc = sum(len(self.group_consistent[g]) for g in self.group_order)
+        self._landmark_inliers()
 
     def _group_ids(self, g):
         a, b, _ = self.group_info(g)
@@ -265,6 +338,8 @@ class PcmGpu:
             if ord(a) in self.ignored or ord(b) in self.ignored:
                 continue
             out.extend(self.group_consistent[g])
+        for lkey in self.landmark_order:  # Pcm.h:996-1002
+            out.extend(self.group_consistent[self.landmark_group[lkey]])
         self.output = out
 
     # ---- the rest of the OutlierRemoval interface ----------------------------------------------
@@ -338,7 +413,10 @@ class PcmGpu:
 
     def groups(self):
         out = []
+        lm = set(self.landmark_group.values())
         for g in range(self.lib.rpgo_num_groups(self.h)):
+            if g in lm:
+                continue  # landmark groups are listed by landmarks()
             a, b, n = self.group_info(g)
             out.append((a, b, n, len(self.group_consistent.get(g, []))))
         return out

@@ -27,7 +27,7 @@
  *
  * Parity pinning: see tests/test_oracle_golden.py (reference test expectations) and
  * tests/test_clique_ref.py (bit-equality with the reference's own FMC sources compiled
- * into oracle/_ref/).  Landmark (special-symbol) re-observations are not restated yet.
+ * into oracle/_ref/).  Landmark (special-symbol) observations: Pcm.h:207-220, :437-455, :775-844.
  */
 #include <algorithm>
 #include <cstdint>
@@ -246,6 +246,12 @@ struct Oracle {
   std::map<uint64_t, opose> values;
   std::vector<ObsId> lc_in_order;
   std::vector<unsigned char> ignored;
+  std::vector<unsigned char> special_symbols;          /* Pcm.h:106 */
+  std::map<uint64_t, Measurements> landmarks;          /* Pcm.h:109 (reference: unordered_map) */
+  std::vector<uint64_t> landmark_order;                /* first-seen order, for output ordering */
+  bool is_special(unsigned char c) const {             /* Pcm.h:506-511 */
+    return std::find(special_symbols.begin(), special_symbols.end(), c) != special_symbols.end();
+  }
   size_t total_lc = 0, total_good_lc = 0;
   int64_t next_id = 0;
   std::vector<int64_t> output;
@@ -393,9 +399,54 @@ struct Oracle {
       }
   }
 
+  /* Pcm.h:775-844.  Observations are (pose key -> landmark key).  A malformed observation (landmark key in
+   * front) makes the reference return before it stores the grown matrices; after that its next growth step
+   * copies a wrongly sized block (undefined behaviour), so the oracle simply refuses the malformed factor. */
+  void increment_landmark_adj(uint64_t lkey) {
+    Measurements& m = landmarks[lkey];
+    const size_t n = m.factors.size();
+    std::vector<double> nadj(n * n, 0.0), ndst(n * n, 0.0);
+    if (n > 1) {
+      const size_t o = (size_t)m.n_adj;
+      for (size_t i = 0; i < o && i + 1 < n; ++i)
+        for (size_t j = 0; j < o && j + 1 < n; ++j) {
+          nadj[i * n + j] = m.adj[i * o + j];
+          ndst[i * n + j] = m.dist[i * o + j];
+        }
+      const Factor& fj = m.factors[n - 1];
+      for (size_t i = 0; i + 1 < n; ++i) {
+        const Factor& fi = m.factors[i];
+        const uint64_t keyi = fi.k1, keyj = fj.k1;
+        OT i_pose_l = ot_from_factor(d, mode, fi.pose, fi.cov);
+        OT j_pose_l = ot_from_factor(d, mode, fj.pose, fj.cov);
+        OT i_odom_j = get_between(key_chr(keyi), keyi, keyj); /* cross-prefix path of GraphUtils.h:43-57 included */
+        OT i_path_l = ot_compose(d, mode, i_odom_j, j_pose_l);
+        OT loop = ot_compose(d, mode, ot_inverse(d, mode, i_path_l), i_pose_l);
+        double dist;
+        const bool ok = check(loop, false, &dist);
+        pair_checks++;
+        note_band(dist, fi.id, fj.id);
+        ndst[(n - 1) * n + i] = ndst[i * n + (n - 1)] = dist;
+        if (ok) nadj[(n - 1) * n + i] = nadj[i * n + (n - 1)] = 1;
+      }
+    }
+    m.adj.swap(nadj);
+    m.dist.swap(ndst);
+    m.n_adj = (int)n;
+  }
+
   void parse_and_increment(const std::vector<Factor>& lcs, std::map<ObsId, size_t>* num_new) { /* Pcm.h:414-502 */
     for (const Factor& f : lcs) {
       if (values.find(f.k1) == values.end() || values.find(f.k2) == values.end()) continue; /* :431-435 */
+      if (is_special(key_chr(f.k1)) || is_special(key_chr(f.k2))) { /* landmark re-observation :440-455 */
+        const uint64_t lkey = is_special(key_chr(f.k1)) ? f.k1 : f.k2;
+        if (f.k1 == lkey) continue; /* malformed (see increment_landmark_adj) */
+        if (landmarks.find(lkey) == landmarks.end()) landmark_order.push_back(lkey);
+        landmarks[lkey].factors.push_back(f);
+        total_lc++;
+        increment_landmark_adj(lkey);
+        continue;
+      }
       double odom_dist;
       bool ok;
       if (key_chr(f.k1) == key_chr(f.k2)) ok = is_odom_consistent(f, &odom_dist); else ok = true;
@@ -429,6 +480,21 @@ struct Oracle {
       }
       total_good_lc += num_inliers;
     }
+    landmark_inliers();
+  }
+
+  /* Pcm.h:878-895 (also :950-966 in the incremental variant): every landmark, full heuristic */
+  void landmark_inliers() {
+    for (auto& kv : landmarks) {
+      Measurements& m = kv.second;
+      std::vector<int> idx;
+      const size_t n = (size_t)m.n_adj;
+      std::vector<double> adj(m.adj.begin(), m.adj.begin() + n * n);
+      const size_t k = (size_t)find_max_clique_heu((int)n, adj.data(), &idx);
+      m.consistent.clear();
+      for (size_t i = 0; i < k; ++i) m.consistent.push_back(m.factors[idx[i]].id);
+      total_good_lc += k;
+    }
   }
 
   void find_inliers_incremental(const std::map<ObsId, size_t>& num_new) { /* Pcm.h:906-970 */
@@ -446,6 +512,7 @@ struct Oracle {
       }
     }
     for (auto& kv : loop_closures) total_good_lc += kv.second.consistent.size();
+    landmark_inliers();
   }
 
   void build_graph() { /* Pcm.h:977-1005: odom, special, consistent LCs of non-ignored groups */
@@ -458,6 +525,10 @@ struct Oracle {
       if (std::find(ignored.begin(), ignored.end(), id.a) != ignored.end()) continue;
       if (std::find(ignored.begin(), ignored.end(), id.b) != ignored.end()) continue;
       output.insert(output.end(), it->second.consistent.begin(), it->second.consistent.end());
+    }
+    for (uint64_t lk : landmark_order) { /* Pcm.h:996-1002 */
+      auto it = landmarks.find(lk);
+      if (it != landmarks.end()) output.insert(output.end(), it->second.consistent.begin(), it->second.consistent.end());
     }
   }
 
@@ -473,7 +544,20 @@ struct Oracle {
     for (Factor& f : nf) {
       f.id = next_id++;
       if (f.type == 0) {
-        if (f.k1 + 1 == f.k2 && new_keys.count(f.k2)) {
+        if (is_special(key_chr(f.k1)) || is_special(key_chr(f.k2))) { /* Pcm.h:180-188 */
+          if (new_keys.count(f.k1) || new_keys.count(f.k2)) {
+            /* FIRST_LANDMARK_OBSERVATION :207-220 */
+            const uint64_t lkey = is_special(key_chr(f.k1)) ? f.k1 : f.k2;
+            if (landmarks.find(lkey) == landmarks.end()) landmark_order.push_back(lkey);
+            Measurements m;
+            m.factors.push_back(f);
+            m.consistent.push_back(f.id);
+            landmarks[lkey] = m;
+            total_lc++;
+          } else if (f.k1 != f.k2) {
+            lcs.push_back(f);
+          }
+        } else if (f.k1 + 1 == f.k2 && new_keys.count(f.k2)) {
           update_odom(f);
         } else {
           if (f.k1 != f.k2) lcs.push_back(f);
@@ -556,6 +640,36 @@ void* orc_create(int d, int mode, const double* thr, int incremental) {
   return o;
 }
 void orc_destroy(void* h) { delete (Oracle*)h; }
+void orc_set_special_symbols(void* h, int n, const unsigned char* syms) {
+  Oracle* o = (Oracle*)h;
+  o->special_symbols.assign(syms, syms + n);
+}
+int orc_num_landmarks(void* h) { return (int)((Oracle*)h)->landmark_order.size(); }
+/* landmark l in first-seen order: key, number of observations, number of inliers */
+void orc_landmark_info(void* h, int l, uint64_t* key, int* n, int* n_inliers) {
+  Oracle* o = (Oracle*)h;
+  const uint64_t k = o->landmark_order[l];
+  const Measurements& m = o->landmarks[k];
+  *key = k;
+  *n = (int)m.factors.size();
+  *n_inliers = (int)m.consistent.size();
+}
+int orc_landmark_adj(void* h, int l, unsigned char* adj, double* dist) {
+  Oracle* o = (Oracle*)h;
+  const Measurements& m = o->landmarks[o->landmark_order[l]];
+  const size_t n = (size_t)m.n_adj;
+  for (size_t i = 0; i < n * n; ++i) {
+    if (adj) adj[i] = m.adj[i] != 0.0;
+    if (dist) dist[i] = m.dist[i];
+  }
+  return (int)n;
+}
+void orc_landmark_ids(void* h, int l, long long* factor_ids, long long* inlier_ids) {
+  Oracle* o = (Oracle*)h;
+  const Measurements& m = o->landmarks[o->landmark_order[l]];
+  if (factor_ids) for (size_t i = 0; i < m.factors.size(); ++i) factor_ids[i] = m.factors[i].id;
+  if (inlier_ids) for (size_t i = 0; i < m.consistent.size(); ++i) inlier_ids[i] = m.consistent[i];
+}
 void orc_set_reference_shaped(void* h, int on) { ((Oracle*)h)->reference_shaped = on != 0; }
 
 /* One removeOutliers() call.  Factors: type (0 between, 1 prior, 2 other), keys, pose (12 or 4

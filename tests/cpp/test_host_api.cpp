@@ -175,12 +175,66 @@ static void RobustSolver_multiRobot(bool simple) {
   EXPECT(pgo->removeLastLoopClosure('c', 'd') == nullptr);
 }
 
+// tests/testLandmark.cpp:23-185 (LandmarkPcm) and :186-348 (LandmarkPcmSimple)
+static void RobustSolver_Landmark(bool simple) {
+  RobustSolverParams params;
+  if (simple) params.setPcmSimple3DParams(0.3, 0.05, Verbosity::QUIET);
+  else params.setPcm3DParams(5.0, 2.5, Verbosity::QUIET);
+  params.specialSymbols = std::vector<char>{'l'};
+  std::unique_ptr<RobustSolver> pgo(new RobustSolver(params));
+  const auto noise = IsotropicVariance(6, 0.1);
+  auto a = [](size_t i) { return Key(Symbol('a', i)); };
+  auto l = [](size_t i) { return Key(Symbol('l', i)); };
+  Values init_vals;
+  init_vals.insert(a(0), Pose3());
+  pgo->update(NonlinearFactorGraph(), init_vals);
+  for (size_t i = 0; i < 5; i++) {
+    Values v; NonlinearFactorGraph f;
+    Pose3 odom(i < 2 ? I3 : R90, 1, 0, 0);
+    v.insert(a(i + 1), odom);
+    f.add(BetweenFactor<Pose3>(a(i), a(i + 1), odom, noise));
+    pgo->update(f, v);
+  }
+  NonlinearFactorGraph lc_factors;
+  lc_factors.add(BetweenFactor<Pose3>(a(3), a(2), Pose3(Pose3::Rz(-1.57), 0, 0.9, 0), noise));
+  lc_factors.add(BetweenFactor<Pose3>(a(4), a(1), Pose3(Pose3::Rz(3.14), 2.1, 1.1, 2.5), noise));
+  pgo->update(lc_factors, Values());
+  EXPECT(pgo->getFactorsUnsafe().size() == size_t(6));
+  EXPECT(pgo->calculateEstimate().size() == size_t(6));
+  // Diagonal::Precisions((0,0,0,25,25,25)): no rotation information (NaN block), translation variance 1/25
+  std::vector<double> lmk_cov(36, 0.0);
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) lmk_cov[i * 6 + j] = std::nan("");
+  for (int i = 3; i < 6; ++i) lmk_cov[i * 6 + i] = 1.0 / 25.0;
+  auto observe = [&](Key from, Key lm, double x, double y, double z, bool first) {
+    NonlinearFactorGraph f; Values v;
+    f.add(BetweenFactor<Pose3>(from, lm, Pose3::Translation(x, y, z), lmk_cov));
+    if (first) v.insert(lm, Pose3::Translation(1, 1, 0));
+    pgo->update(f, v);
+  };
+  observe(a(1), l(0), 0, 1, 0, true);
+  EXPECT(pgo->getFactorsUnsafe().size() == size_t(7));
+  EXPECT(pgo->calculateEstimate().size() == size_t(7));
+  observe(a(5), l(0), 0, -1, 0, false);   // consistent re-observation
+  EXPECT(pgo->getFactorsUnsafe().size() == size_t(8));
+  observe(a(4), l(0), 1, 0, 0, false);    // inconsistent re-observation
+  EXPECT(pgo->getFactorsUnsafe().size() == size_t(8));
+  EXPECT(pgo->calculateEstimate().size() == size_t(7));
+  observe(a(2), l(1), 0, -1, 0, true);
+  EXPECT(pgo->getFactorsUnsafe().size() == size_t(9));
+  EXPECT(pgo->calculateEstimate().size() == size_t(8));
+  observe(a(5), l(1), 2, 0, 0, false);
+  EXPECT(pgo->getFactorsUnsafe().size() == size_t(10));
+  EXPECT(pgo->calculateEstimate().size() == size_t(8));
+}
+
 int main() {
   try {
     Pcm_OdometryCheck();
     Pcm_ConsistencyCheck();
     RobustSolver_multiRobot(false);
     RobustSolver_multiRobot(true);
+    RobustSolver_Landmark(false);
+    RobustSolver_Landmark(true);
   } catch (const std::exception& e) {
     std::printf("EXCEPTION %s\n", e.what());
     return 2;

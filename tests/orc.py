@@ -30,6 +30,13 @@ def lib():
         L.orc_create.argtypes = [C.c_int, C.c_int, c_dp, C.c_int]
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_set_reference_shaped.argtypes = [C.c_void_p, C.c_int]
+        L.orc_set_special_symbols.argtypes = [C.c_void_p, C.c_int, c_u8p]
+        L.orc_num_landmarks.restype = C.c_int
+        L.orc_num_landmarks.argtypes = [C.c_void_p]
+        L.orc_landmark_info.argtypes = [C.c_void_p, C.c_int, c_u64p, c_ip, c_ip]
+        L.orc_landmark_adj.restype = C.c_int
+        L.orc_landmark_adj.argtypes = [C.c_void_p, C.c_int, c_u8p, c_dp]
+        L.orc_landmark_ids.argtypes = [C.c_void_p, C.c_int, c_llp, c_llp]
         L.orc_update.restype = C.c_int
         L.orc_update.argtypes = [C.c_void_p, C.c_int, c_ip, c_u64p, c_u64p, c_dp, c_dp, C.c_int, c_u64p, c_dp]
         for n in ["orc_num_lc", "orc_num_inliers", "orc_num_odom", "orc_num_special", "orc_num_values",
@@ -252,10 +259,13 @@ class OraclePcm:
     """Pcm<poseT, T> restated (reference: include/KimeraRPGO/outlier/Pcm.h).  d: 2|3, mode: 0 PCM, 1 Simple."""
 
     def __init__(self, d, mode, odom_threshold=10.0, lc_threshold=5.0, odom_trans=0.05, odom_rot=0.005,
-                 dist_trans=0.01, dist_rot=0.001, incremental=False):
+                 dist_trans=0.01, dist_rot=0.001, incremental=False, special_symbols=()):
         self.d, self.mode = d, mode
         thr = np.array([odom_threshold, lc_threshold, odom_trans, odom_rot, dist_trans, dist_rot], dtype=np.float64)
         self.h = lib().orc_create(d, mode, dp(thr), int(incremental))
+        if special_symbols:
+            sy = np.array([ord(c) for c in special_symbols], dtype=np.uint8)
+            lib().orc_set_special_symbols(self.h, len(sy), sy.ctypes.data_as(c_u8p))
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -334,6 +344,27 @@ class OraclePcm:
         ids = np.zeros(max(n, 1), dtype=np.int64)
         lib().orc_group_inlier_ids(self.h, g, ids.ctypes.data_as(c_llp))
         return ids[:n]
+
+    def landmarks(self):
+        """[(key, n_observations, n_inliers)] in first-seen order"""
+        out = []
+        for l in range(lib().orc_num_landmarks(self.h)):
+            k, n, ni = C.c_uint64(), C.c_int(), C.c_int()
+            lib().orc_landmark_info(self.h, l, C.byref(k), C.byref(n), C.byref(ni))
+            out.append((k.value, n.value, ni.value))
+        return out
+
+    def landmark_adj(self, l):
+        n = lib().orc_landmark_adj(self.h, l, None, None)
+        adj = np.zeros((n, n), dtype=np.uint8); dist = np.zeros((n, n))
+        lib().orc_landmark_adj(self.h, l, adj.ctypes.data_as(c_u8p), dp(dist))
+        return adj, dist
+
+    def landmark_ids(self, l):
+        _, n, ni = self.landmarks()[l]
+        f = np.zeros(max(n, 1), dtype=np.int64); i = np.zeros(max(ni, 1), dtype=np.int64)
+        lib().orc_landmark_ids(self.h, l, f.ctypes.data_as(c_llp), i.ctypes.data_as(c_llp))
+        return f[:n], i[:ni]
 
     def flagged(self):
         n = lib().orc_num_flagged(self.h)

@@ -126,6 +126,36 @@ def multi_robot(simple=False):
     return 3, (1 if simple else 0), params, calls, expect
 
 
+def landmark_pcm(simple=False):
+    """tests/testLandmark.cpp:23-196 (Pcm3D 5.0/2.5) — special symbol 'l', NaN rotation covariance (rotation_info=false)."""
+    a = lambda i: sym('a', i)
+    l = lambda i: sym('l', i)
+    calls = [([], [(a(0), pose3())])]
+    for i in range(2):
+        p = pose3(None, (1, 0, 0))
+        calls.append(([(BETWEEN, a(i), a(i + 1), p, 0.1 * I6)], [(a(i + 1), p)]))
+    for i in range(2, 5):
+        p = pose3(R90, (1, 0, 0))
+        calls.append(([(BETWEEN, a(i), a(i + 1), p, 0.1 * I6)], [(a(i + 1), p)]))
+    calls.append(([(BETWEEN, a(3), a(2), pose3(Rz(-1.57), (0, 0.9, 0)), 0.1 * I6),
+                   (BETWEEN, a(4), a(1), pose3(Rz(3.14), (2.1, 1.1, 2.5)), 0.1 * I6)], []))
+    n0 = len(calls) - 1
+    lcov = np.full((6, 6), 0.0)
+    lcov[:3, :3] = np.nan       # Diagonal::Precisions((0,0,0,25,25,25)).covariance(): no rotation information
+    lcov[3:, 3:] = np.eye(3) / 25.0
+    calls.append(([(BETWEEN, a(1), l(0), pose3(None, (0, 1, 0)), lcov)], [(l(0), pose3(None, (1, 1, 0)))]))
+    calls.append(([(BETWEEN, a(5), l(0), pose3(None, (0, -1, 0)), lcov)], []))
+    calls.append(([(BETWEEN, a(4), l(0), pose3(None, (1, 0, 0)), lcov)], []))
+    calls.append(([(BETWEEN, a(2), l(1), pose3(None, (0, -1, 0)), lcov)], [(l(1), pose3(None, (1, 1, 0)))]))
+    calls.append(([(BETWEEN, a(5), l(1), pose3(None, (2, 0, 0)), lcov)], []))
+    if simple:  # tests/testLandmark.cpp:186-348: same graph, setPcmSimple3DParams(0.3, 0.05)
+        params = dict(odom_trans=0.3, odom_rot=0.05, dist_trans=0.3, dist_rot=0.05, special_symbols=('l',))
+    else:
+        params = dict(odom_threshold=5.0, lc_threshold=2.5, special_symbols=('l',))
+    expect = {n0: (6, 6), n0 + 1: (7, 7), n0 + 2: (8, 7), n0 + 3: (8, 7), n0 + 4: (9, 8), n0 + 5: (10, 8)}
+    return 3, (1 if simple else 0), params, calls, expect
+
+
 _G2O = None
 
 
@@ -171,6 +201,8 @@ ALL = {
     "simple_consistency_rot_check": simple_consistency_rot_check,
     "multi_robot_pcm": lambda: multi_robot(False),
     "multi_robot_simple": lambda: multi_robot(True),
+    "landmark_pcm": landmark_pcm,
+    "landmark_simple": lambda: landmark_pcm(True),
     "load1": lambda: load_graph_calls("load1"),
     "add1": lambda: load_graph_calls("add1"),
     "load2": lambda: load_graph_calls("load2"),

@@ -25,7 +25,23 @@ def run_both(d, mode, params, calls, expect=None, **gpu_kw):
     return o, g
 
 
+def compare_landmarks(o, g):
+    """landmark groups: same landmarks, adjacency, distances and inlier ids"""
+    ol, gl = o.landmarks(), g.landmarks()
+    assert ol == gl, (ol, gl)
+    for l, (key, n, ni) in enumerate(ol):
+        ao, do = o.landmark_adj(l)
+        gi = g.landmark_group[key]
+        ag, dg = g.group_adj(gi, with_dist=True)
+        assert ao.shape[0] == n and np.array_equal(ao, ag), ("landmark adjacency", l)
+        iu = np.triu_indices(n, 1)
+        assert np.array_equal(do[iu], dg[iu], equal_nan=True), ("landmark distances", l)
+        fo, io = o.landmark_ids(l)
+        assert fo.tolist() == g.group_factor_ids(gi).tolist() and io.tolist() == g.group_inlier_ids(gi).tolist()
+
+
 def compare_groups(o, g, check_dist=True):
+    compare_landmarks(o, g)
     og, gg = o.groups(), g.groups()
     assert [(a, b, n) for a, b, n, _ in og] == [(a, b, n) for a, b, n, _ in gg]
     for gi in range(len(og)):
@@ -387,3 +403,38 @@ def test_straight_line_kernel_equals_direct_kernel():
         g.close()
     assert np.array_equal(bits[0][0], bits[1][0]) and bits[0][1] == bits[1][1]
     assert np.array_equal(bits[0][0], bits[2][0]) and bits[0][1] == bits[2][1]
+
+
+def test_landmarks_two_robots_and_many_observations():
+    """landmark observations from two robots (getBetween's different-prefix path, GraphUtils.h:43-57, as the
+    reference runs it) and a landmark with > 32 observations (several adjacency words), Pcm3D and PcmSimple3D."""
+    rng = np.random.default_rng(31)
+    a = lambda i: orc.sym('a', i)
+    b = lambda i: orc.sym('b', i)
+    l = lambda i: orc.sym('l', i)
+    I6 = np.eye(6)
+    lcov = np.zeros((6, 6)); lcov[:3, :3] = np.nan; lcov[3:, 3:] = 0.04 * np.eye(3)
+    full = 0.05 * I6
+    calls = [([], [(a(0), orc.pose3()), (b(0), orc.pose3(None, (0, -2, 0)))])]
+    P = 45
+    for i in range(P):
+        pa = orc.pose3(orc.Rz(0.05), (1, 0, 0)); pb = orc.pose3(orc.Rz(-0.03), (1, 0.1, 0))
+        calls.append(([(orc.BETWEEN, a(i), a(i + 1), pa, 0.01 * I6), (orc.BETWEEN, b(i), b(i + 1), pb, 0.01 * I6)],
+                      [(a(i + 1), pa), (b(i + 1), pb)]))
+    # landmark 0: first seen by a, re-observed by a and b; landmark 1: 40 observations, half of them with full covariance
+    calls.append(([(orc.BETWEEN, a(2), l(0), orc.pose3(None, (0, 1, 0)), lcov)], [(l(0), orc.pose3())]))
+    calls.append(([(orc.BETWEEN, a(9), l(0), orc.pose3(None, (0.3, 1, 0)), lcov),
+                   (orc.BETWEEN, b(4), l(0), orc.pose3(None, (0, 2, 0)), lcov),
+                   (orc.BETWEEN, b(7), l(0), orc.pose3(None, (1, 2, 0)), full)], []))
+    calls.append(([(orc.BETWEEN, a(1), l(1), orc.pose3(None, (5, 5, 0)), lcov)], [(l(1), orc.pose3())]))
+    obs = []
+    for k in range(40):
+        t = rng.normal(size=3) * (0.2 if k % 3 else 4.0) + np.array([5.0 - k * 0.9, 5, 0])
+        obs.append((orc.BETWEEN, a(2 + k), l(1), orc.pose3(orc.Rz(rng.normal() * 0.1), t), lcov if k % 2 else full))
+    calls.append((obs[:7], []))
+    calls.append((obs[7:], []))
+    for mode, params in [(0, dict(odom_threshold=-1, lc_threshold=3.0)),
+                         (1, dict(odom_trans=-1, odom_rot=-1, dist_trans=0.2, dist_rot=0.05))]:
+        o, g = run_both(3, mode, dict(params, special_symbols=('l',)), calls)
+        compare_groups(o, g)
+        assert len(o.landmarks()) == 2 and o.landmarks()[1][1] == 41
