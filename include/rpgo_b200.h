@@ -144,6 +144,19 @@ int rpgo_lc_remove_last(rpgo_handle* h, int32_t g, uint64_t* key_from, uint64_t*
 int rpgo_find_inliers(rpgo_handle* h, int32_t g, int32_t clique_mode, int64_t n_new, int64_t prev_size,
                       int32_t* ids_out, int64_t* size_out, int32_t* true_clique_out);
 
+/* ---- N4: multi-robot frame alignment, the batched front half (Pcm::multirobotValueInitialization,
+ * Pcm.h:1024-1055; the GNC pose averaging that follows stays on GTSAM) -------------------------------------
+ * For the m closures closure_idx[] of group g (normally its inliers) writes T_w0_wi = T_w0_front . T_front_back .
+ * T_wi_back^-1, swapping the keys and inverting the measurement when the closure is stated ri -> r0 (:1043-1048).
+ * Returns RPGO_ERR_NOT_FOUND if a key has no trajectory entry (the reference's .at() throws and the robot is
+ * skipped, :1060-1064). */
+int rpgo_frame_align_measurements(rpgo_handle* h, int32_t g, uint8_t r0, int64_t m, const int32_t* closure_idx,
+                                  double* T_w0_wi_out);
+/* getRobotOdomValues (Pcm.h:1074-1082): transform . pose for every trajectory entry of `prefix` in ascending
+ * key order (transform may be NULL = identity).  Call with keys_out = poses_out = NULL to get the count. */
+int rpgo_robot_odom_values(rpgo_handle* h, uint8_t prefix, const double* transform, int64_t cap, uint64_t* keys_out,
+                           double* poses_out, int64_t* n_out);
+
 /* ---- parity / inspection ---------------------------------------------------------------------- */
 /* copy group g's adjacency to the host: n rows of stride_words 64-bit words (stride_words >= ceil(n/64)) */
 int rpgo_adj_bits(rpgo_handle* h, int32_t g, uint64_t* rows_out, int64_t stride_words);

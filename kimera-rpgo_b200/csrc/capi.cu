@@ -1114,6 +1114,66 @@ int rpgo_debug_load_group(rpgo_handle* h, uint8_t id1, uint8_t id2, int64_t n, c
   return RPGO_OK;
 }
 
+int rpgo_frame_align_measurements(rpgo_handle* h, int32_t gi, uint8_t r0, int64_t m, const int32_t* closure_idx,
+                                  double* T_out) {
+  if (!h || m < 0 || (m > 0 && (!closure_idx || !T_out))) return RPGO_ERR_INVALID;
+  if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
+  Group* g = h->groups[gi];
+  if (g->landmark) return RPGO_ERR_INVALID;
+  if (m == 0) return RPGO_OK;
+  for (int64_t t = 0; t < m; ++t) {
+    const int32_t c = closure_idx[t];
+    if (c < 0 || c >= g->n) return RPGO_ERR_INVALID;
+    if (!h->key2idx.count(g->kfrom[c]) || !h->key2idx.count(g->kto[c])) {
+      h->err = "frame alignment: closure key without trajectory entry";
+      return RPGO_ERR_NOT_FOUND;
+    }
+  }
+  cudaStream_t st = h->stream;
+  const size_t ib = ((size_t)m * 4 + 255) & ~size_t(255);
+  H_CHECK_CUDA(h, h->d_stage.ensure(ib + (size_t)m * h->PS * 8, 0, st));
+  H_CHECK_CUDA(h, cudaMemcpyAsync(h->d_stage.p, closure_idx, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+  double* d_out = (double*)((char*)h->d_stage.p + ib);
+  launch_frame_align(h->dim, group_view(h, g), h->traj.as<double>(), h->E, r0, (int)m, (const int32_t*)h->d_stage.p, d_out, st);
+  h->launches++;
+  H_CHECK_CUDA(h, cudaGetLastError());
+  H_CHECK_CUDA(h, cudaMemcpyAsync(T_out, d_out, (size_t)m * h->PS * 8, cudaMemcpyDeviceToHost, st));
+  H_CHECK_CUDA(h, cudaStreamSynchronize(st));
+  return RPGO_OK;
+}
+
+int rpgo_robot_odom_values(rpgo_handle* h, uint8_t prefix, const double* transform, int64_t cap, uint64_t* keys_out,
+                           double* poses_out, int64_t* n_out) {
+  if (!h || !n_out) return RPGO_ERR_INVALID;
+  std::vector<std::pair<uint64_t, int32_t>> ent;
+  for (auto& kv : h->key2idx)
+    if (key_chr(kv.first) == prefix) ent.push_back({kv.first, kv.second});
+  std::sort(ent.begin(), ent.end());
+  *n_out = (int64_t)ent.size();
+  if (!keys_out && !poses_out) return RPGO_OK;
+  if (cap < (int64_t)ent.size() || !keys_out || !poses_out) return RPGO_ERR_INVALID;
+  const int64_t m = (int64_t)ent.size();
+  if (m == 0) return RPGO_OK;
+  std::vector<int32_t> idx((size_t)m);
+  for (int64_t i = 0; i < m; ++i) { keys_out[i] = ent[i].first; idx[i] = ent[i].second; }
+  std::vector<double> T(h->PS, 0.0);
+  if (transform) memcpy(T.data(), transform, sizeof(double) * h->PS);
+  else if (h->dim == 3) { T[0] = T[4] = T[8] = 1.0; } else { T[0] = 1.0; }
+  cudaStream_t st = h->stream;
+  const size_t ib = ((size_t)m * 4 + 255) & ~size_t(255), tb = 256;
+  H_CHECK_CUDA(h, h->d_stage.ensure(ib + tb + (size_t)m * h->PS * 8, 0, st));
+  char* d = (char*)h->d_stage.p;
+  H_CHECK_CUDA(h, cudaMemcpyAsync(d, idx.data(), (size_t)m * 4, cudaMemcpyHostToDevice, st));
+  H_CHECK_CUDA(h, cudaMemcpyAsync(d + ib, T.data(), sizeof(double) * h->PS, cudaMemcpyHostToDevice, st));
+  double* d_out = (double*)(d + ib + tb);
+  launch_transform_poses(h->dim, h->traj.as<double>(), h->E, (int)m, (const int32_t*)d, (const double*)(d + ib), d_out, st);
+  h->launches++;
+  H_CHECK_CUDA(h, cudaGetLastError());
+  H_CHECK_CUDA(h, cudaMemcpyAsync(poses_out, d_out, (size_t)m * h->PS * 8, cudaMemcpyDeviceToHost, st));
+  H_CHECK_CUDA(h, cudaStreamSynchronize(st));
+  return RPGO_OK;
+}
+
 int rpgo_debug_check_fastmath(int64_t n, uint64_t seed, uint64_t* mismatches, uint64_t* checked) {
   if (!mismatches || !checked || n <= 0) return RPGO_ERR_INVALID;
   int ndev = 0;

@@ -65,6 +65,11 @@ void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, co
 /* N3: landmark re-observation matrix (one thread per pair of observations of the same landmark) */
 void launch_landmark_direct(int dim, int mode, GroupView g, const double* traj, int j_begin, Thresholds th, Flagged fl,
                             double* dist_out, cudaStream_t st);
+/* N4: frame-alignment measurements and transformed trajectories (pose-only batched kernels) */
+void launch_frame_align(int dim, GroupView g, const double* traj, int entry, uint8_t r0, int m, const int32_t* closure_idx,
+                        double* out, cudaStream_t st);
+void launch_transform_poses(int dim, const double* traj, int entry, int m, const int32_t* entry_idx, const double* transform,
+                            double* out, cudaStream_t st);
 /* bitset maintenance */
 void launch_mirror(uint32_t* bits, int64_t stride32, int n, int j_begin, cudaStream_t st);
 void launch_degree(const uint32_t* bits, int64_t stride32, int n, int32_t* deg, cudaStream_t st);

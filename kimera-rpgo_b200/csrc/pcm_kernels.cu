@@ -477,6 +477,59 @@ void launch_landmark_direct(int dim, int mode, GroupView g, const double* traj, 
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * N4: multi-robot frame alignment, front half (Pcm.h:1024-1055) and getRobotOdomValues (Pcm.h:1074-1082).
+ * One thread per closure / trajectory entry; pose arithmetic only.
+ * ---------------------------------------------------------------------------------------------- */
+template <int D>
+__global__ void frame_align_kernel(GroupView g, const double* __restrict__ traj, int E, uint8_t r0, int m,
+                                   const int32_t* __restrict__ closure_idx, double* out) {
+  constexpr int PS = Dim<D>::PS;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  const int c = closure_idx[t];
+  Pose<D> Tfb, Tf, Tb;
+  load_pose<D>(g.lc + (size_t)c * E, 1, Tfb);
+  int ifr = g.idx_front[c], ibk = g.idx_back[c];
+  if (g.pfx_front[c] != r0) { /* closure stated ri -> r0: swap the keys and invert the measurement */
+    const int tmp = ifr; ifr = ibk; ibk = tmp;
+    Tfb = inverse<D>(Tfb);
+  }
+  load_pose<D>(traj + (size_t)ifr * E, 1, Tf);
+  load_pose<D>(traj + (size_t)ibk * E, 1, Tb);
+  const Pose<D> r = compose<D>(compose<D>(Tf, Tfb), inverse<D>(Tb));
+#pragma unroll
+  for (int i = 0; i < PS; ++i) out[(size_t)t * PS + i] = r.m[i];
+}
+void launch_frame_align(int dim, GroupView g, const double* traj, int entry, uint8_t r0, int m, const int32_t* closure_idx,
+                        double* out, cudaStream_t st) {
+  if (m <= 0) return;
+  const int T = 128;
+  if (dim == 3) frame_align_kernel<3><<<(m + T - 1) / T, T, 0, st>>>(g, traj, entry, r0, m, closure_idx, out);
+  else frame_align_kernel<2><<<(m + T - 1) / T, T, 0, st>>>(g, traj, entry, r0, m, closure_idx, out);
+}
+
+template <int D>
+__global__ void transform_poses_kernel(const double* __restrict__ traj, int E, int m, const int32_t* __restrict__ entry_idx,
+                                       const double* __restrict__ transform, double* out) {
+  constexpr int PS = Dim<D>::PS;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  Pose<D> T, P;
+  load_pose<D>(transform, 1, T);
+  load_pose<D>(traj + (size_t)entry_idx[t] * E, 1, P);
+  const Pose<D> r = compose<D>(T, P);
+#pragma unroll
+  for (int i = 0; i < PS; ++i) out[(size_t)t * PS + i] = r.m[i];
+}
+void launch_transform_poses(int dim, const double* traj, int entry, int m, const int32_t* entry_idx, const double* transform,
+                            double* out, cudaStream_t st) {
+  if (m <= 0) return;
+  const int T = 128;
+  if (dim == 3) transform_poses_kernel<3><<<(m + T - 1) / T, T, 0, st>>>(traj, entry, m, entry_idx, transform, out);
+  else transform_poses_kernel<2><<<(m + T - 1) / T, T, 0, st>>>(traj, entry, m, entry_idx, transform, out);
+}
+
+/* ------------------------------------------------------------------------------------------------
  * mirror: fill row j (columns i < j) from column j of rows i < j, for rows j >= j_begin.
  * One warp transposes a 32x32 bit block with 32 ballots.
  * ---------------------------------------------------------------------------------------------- */

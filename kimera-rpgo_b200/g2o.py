@@ -74,3 +74,51 @@ def load2d(path):
                 m = _upper_tri([float(v) for v in p[6:12]], 3)
                 edges.append((k1, k2, np.array([np.cos(th), np.sin(th), x, y]), np.linalg.inv(m)))
     return values, edges
+
+
+def R_to_quat(R):
+    """rotation matrix -> (qx, qy, qz, qw), w >= 0 branch-stable (Shepperd)"""
+    R = np.asarray(R, dtype=np.float64).reshape(3, 3)
+    tr = R[0, 0] + R[1, 1] + R[2, 2]
+    if tr > 0:
+        s = np.sqrt(tr + 1.0) * 2
+        w, x, y, z = 0.25 * s, (R[2, 1] - R[1, 2]) / s, (R[0, 2] - R[2, 0]) / s, (R[1, 0] - R[0, 1]) / s
+    elif R[0, 0] > R[1, 1] and R[0, 0] > R[2, 2]:
+        s = np.sqrt(1.0 + R[0, 0] - R[1, 1] - R[2, 2]) * 2
+        w, x, y, z = (R[2, 1] - R[1, 2]) / s, 0.25 * s, (R[0, 1] + R[1, 0]) / s, (R[0, 2] + R[2, 0]) / s
+    elif R[1, 1] > R[2, 2]:
+        s = np.sqrt(1.0 + R[1, 1] - R[0, 0] - R[2, 2]) * 2
+        w, x, y, z = (R[0, 2] - R[2, 0]) / s, (R[0, 1] + R[1, 0]) / s, 0.25 * s, (R[1, 2] + R[2, 1]) / s
+    else:
+        s = np.sqrt(1.0 + R[2, 2] - R[0, 0] - R[1, 1]) * 2
+        w, x, y, z = (R[1, 0] - R[0, 1]) / s, (R[0, 2] + R[2, 0]) / s, (R[1, 2] + R[2, 1]) / s, 0.25 * s
+    return x, y, z, w
+
+
+def write_g2o(path, values, edges, d=3):
+    """Egress in the record layout of the reference's writeG2o (src/Logger.cpp:64-163): VERTEX_SE3:QUAT / VERTEX_SE2
+    lines for the values, then EDGE_SE3:QUAT / EDGE_SE2 lines with the upper triangle of the information matrix in
+    g2o order (translation first for SE3).  edges: (key1, key2, pose, cov); numbers are written with 17 significant
+    digits so that a round trip through load3d / load2d is lossless (the reference uses the stream default)."""
+    f17 = lambda v: "%.17g" % v
+    with open(path, "w") as f:
+        for key, p in values:
+            if d == 3:
+                q = R_to_quat(np.asarray(p[:9]))
+                f.write("VERTEX_SE3:QUAT %d %s\n" % (key, " ".join(f17(v) for v in list(p[9:12]) + list(q))))
+            else:
+                f.write("VERTEX_SE2 %d %s\n" % (key, " ".join(f17(v) for v in (p[2], p[3], np.arctan2(p[1], p[0])))))
+        for k1, k2, p, cov in edges:
+            info = np.linalg.inv(np.asarray(cov, dtype=np.float64))
+            if d == 3:
+                q = R_to_quat(np.asarray(p[:9]))
+                g = np.zeros((6, 6))
+                g[0:3, 0:3] = info[3:6, 3:6]
+                g[3:6, 3:6] = info[0:3, 0:3]
+                g[0:3, 3:6] = info[0:3, 3:6]
+                g[3:6, 0:3] = info[3:6, 0:3]
+                tri = [g[i, j] for i in range(6) for j in range(i, 6)]
+                f.write("EDGE_SE3:QUAT %d %d %s\n" % (k1, k2, " ".join(f17(v) for v in list(p[9:12]) + list(q) + tri)))
+            else:
+                tri = [info[i, j] for i in range(3) for j in range(i, 3)]
+                f.write("EDGE_SE2 %d %d %s\n" % (k1, k2, " ".join(f17(v) for v in [p[2], p[3], np.arctan2(p[1], p[0])] + tri)))

@@ -78,6 +78,32 @@ class PcmGpu:
         self.next_id = 0
         self.output = []
 
+    # ---- logging in the reference's on-disk formats (OutlierRemoval.h:54-62, Pcm.h:1136-1164,
+    #      RobustSolver.cpp:93-102, :359-367) -------------------------------------------------------
+    def log_output(self, folder):
+        import os
+        self.log_folder = folder
+        os.makedirs(folder, exist_ok=True)
+        with open(os.path.join(folder, "outlier_rejection_status.txt"), "w") as f:
+            f.write("total inliers spin-time mc-time\n")
+        with open(os.path.join(folder, "rpgo_status.csv"), "w") as f:
+            f.write("graph-size,spin-time(mu-s),num-lc,num-inliers\n")
+
+    def _log_spin(self, spin_s, clique_s):
+        import os
+        folder = getattr(self, "log_folder", None)
+        if not folder:
+            return
+        for g in self.group_order:  # saveAdjacencyMatrix: "<id1>-<id2>_adj_matrix.txt", dense rows
+            a, b, n = self.group_info(g)
+            if 0 < n <= 4096 and self.loop_check:
+                adj, _ = self.group_adj(g, with_dist=False)
+                np.savetxt(os.path.join(folder, "%s-%s_adj_matrix.txt" % (a, b)), adj, fmt="%d")
+        with open(os.path.join(folder, "outlier_rejection_status.txt"), "a") as f:  # logSpinStatus
+            f.write("%d %d %d %d\n" % (self.total_lc, self.total_good_lc, int(spin_s * 1e3), int(clique_s * 1e3)))
+        with open(os.path.join(folder, "rpgo_status.csv"), "a") as f:  # RobustSolver::update
+            f.write("%d,%d,%d,%d\n" % (len(self.output), int(spin_s * 1e6), self.total_lc, self.total_good_lc))
+
     def close(self):
         if getattr(self, "h", None) is not None and self.h:
             self.lib.rpgo_destroy(self.h)
@@ -96,6 +122,9 @@ class PcmGpu:
     # ---- OutlierRemoval::removeOutliers (Pcm.h:148-281) ---------------------------------------
     def update(self, factors, values):
         """One removeOutliers() call.  Returns do_optimize."""
+        import time
+        t_start = time.perf_counter()
+        t_clique = 0.0
         new_keys = set()
         for k, p in values:
             self.values[int(k)] = np.asarray(p, dtype=np.float64)
@@ -135,12 +164,16 @@ class PcmGpu:
                 lcs = [l for l, m in zip(lcs, is_lm) if not m]
                 self._landmark_reobserve(lm)
             num_new = self._lc_append(lcs) if lcs else {}
+            t0 = time.perf_counter()
             if self.incremental:
                 self._find_inliers_incremental(num_new)
             else:
                 self._find_inliers()
+            t_clique = time.perf_counter() - t0
             do_optimize = True
         self._build_graph()
+        if getattr(self, "log_folder", None):
+            self._log_spin(time.perf_counter() - t_start, t_clique)
         return do_optimize
 
     def _odom_append(self, odom):
@@ -382,6 +415,36 @@ class PcmGpu:
         self.nfg_special = [f for f in self.nfg_special
                             if not (f in self.special_is_prior and key_chr(self.special_is_prior[f]) == ord(c))]
         self._build_graph()
+
+    # ---- N4: multi-robot frame alignment, front half (Pcm.h:1024-1082) ------------------------------
+    def frame_align_measurements(self, r0, ri):
+        """T_w0_wi for every inlier closure of group (r0, ri); None when the group / a trajectory key is missing
+        (the reference logs a warning and skips the robot)."""
+        g = self.lib.rpgo_find_group(self.h, ord(r0), ord(ri))
+        if g < 0 or g not in self.group_factors:
+            return None
+        fs = self.group_factors[g]
+        idx = np.array([fs.index(f) for f in self.group_consistent[g]], dtype=np.int32)
+        out = np.zeros((max(len(idx), 1), self.ps))
+        rc = self.lib.rpgo_frame_align_measurements(self.h, g, ord(r0), len(idx), idx.ctypes.data_as(_capi.c_i32p), _dp(out))
+        if rc == 4:
+            return None
+        self._check(rc, "rpgo_frame_align_measurements")
+        return out[:len(idx)]
+
+    def robot_odom_values(self, prefix, transform=None):
+        """getRobotOdomValues: (keys, transform . pose) for the trajectory of `prefix`, ascending keys."""
+        n = C.c_int64()
+        self._check(self.lib.rpgo_robot_odom_values(self.h, ord(prefix), None, 0, None, None, C.byref(n)), "rpgo_robot_odom_values")
+        keys = np.zeros(max(n.value, 1), dtype=np.uint64)
+        poses = np.zeros((max(n.value, 1), self.ps))
+        tp = None
+        if transform is not None:
+            transform = np.ascontiguousarray(transform, dtype=np.float64)
+            tp = _dp(transform)
+        self._check(self.lib.rpgo_robot_odom_values(self.h, ord(prefix), tp, n.value, keys.ctypes.data_as(_capi.c_u64p),
+                                                    _dp(poses), C.byref(n)), "rpgo_robot_odom_values")
+        return keys[:n.value], poses[:n.value]
 
     # counters: OutlierRemoval.h:24-27
     def num_lc(self):

@@ -86,6 +86,8 @@ def loop_closures_3d(rng, ga, gb, n, outlier_frac, sig_r2=1e-3, sig_t2=1e-2, min
     i = rng.integers(0, ga.P, size=n)
     j = rng.integers(0, gb.P, size=n)
     if same:
+        if ga.P <= 2 * min_sep + 1:
+            raise ValueError("need P > 2*min_sep+1 poses to draw separated closures")
         bad = np.abs(i - j) <= min_sep
         while bad.any():
             j[bad] = rng.integers(0, gb.P, size=int(bad.sum()))
@@ -173,6 +175,8 @@ def config3(seed=2, P=10000, n=10000, outlier_frac=0.3):
         cxy = cxy + np.array([c * o_xy[k, 0] - s * o_xy[k, 1], s * o_xy[k, 0] + c * o_xy[k, 1]])
         cth = cth + o_th[k]
         values.append((keys[k + 1], np.array([np.cos(cth), np.sin(cth), cxy[0], cxy[1]])))
+    if P <= 41:
+        raise ValueError("need P > 41 poses to draw separated closures")
     i = rng.integers(0, P, size=n); j = rng.integers(0, P, size=n)
     bad = np.abs(i - j) <= 20
     while bad.any():

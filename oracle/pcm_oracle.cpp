@@ -644,6 +644,63 @@ void orc_set_special_symbols(void* h, int n, const unsigned char* syms) {
   Oracle* o = (Oracle*)h;
   o->special_symbols.assign(syms, syms + n);
 }
+/* N4, multirobotValueInitialization front half (Pcm.h:1024-1055): T_w0_wi = T_w0_front . T_front_back . T_wi_back^-1 for
+ * every consistent closure of group (r0, ri).  Returns the number written, or -1 when a trajectory key is missing
+ * (the reference's .at() throws and the robot is skipped). */
+int orc_frame_align(void* h, int r0, int ri, double* out) {
+  Oracle* o = (Oracle*)h;
+  auto it = o->loop_closures.find(make_obs((unsigned char)r0, (unsigned char)ri));
+  if (it == o->loop_closures.end()) return -1;
+  const int ps = o->d == 3 ? 12 : 4;
+  int n = 0;
+  for (int64_t fid : it->second.consistent) {
+    const Factor* f = nullptr;
+    for (const Factor& q : it->second.factors) if (q.id == fid) f = &q;
+    uint64_t front = f->k1, back = f->k2;
+    opose T_fb;
+    memset(&T_fb, 0, sizeof(T_fb));
+    memcpy(T_fb.m, f->pose, sizeof(double) * ps);
+    if (key_chr(front) != (unsigned char)r0) {
+      std::swap(front, back);
+      opose inv;
+      o_pose_inverse(o->d, &T_fb, &inv);
+      T_fb = inv;
+    }
+    auto t0 = o->traj.find((unsigned char)r0), ti = o->traj.find((unsigned char)ri);
+    if (t0 == o->traj.end() || ti == o->traj.end()) return -1;
+    auto pf = t0->second.find(front), pb = ti->second.find(back);
+    if (pf == t0->second.end() || pb == ti->second.end()) return -1;
+    const opose& Tf = o->mode == MODE_PCM ? pf->second.c.pose : pf->second.s.pose;
+    const opose& Tb = o->mode == MODE_PCM ? pb->second.c.pose : pb->second.s.pose;
+    opose tmp, Tbinv, res;
+    o_pose_compose(o->d, &Tf, &T_fb, &tmp);
+    o_pose_inverse(o->d, &Tb, &Tbinv);
+    o_pose_compose(o->d, &tmp, &Tbinv, &res);
+    memcpy(out + (size_t)n * ps, res.m, sizeof(double) * ps);
+    ++n;
+  }
+  return n;
+}
+/* getRobotOdomValues (Pcm.h:1074-1082): transform . pose for every trajectory entry, ascending key order */
+int orc_robot_odom_values(void* h, int prefix, const double* transform, uint64_t* keys, double* poses) {
+  Oracle* o = (Oracle*)h;
+  auto t = o->traj.find((unsigned char)prefix);
+  if (t == o->traj.end()) return -1;
+  const int ps = o->d == 3 ? 12 : 4;
+  opose T;
+  o_pose_identity(o->d, &T);
+  if (transform) memcpy(T.m, transform, sizeof(double) * ps);
+  int n = 0;
+  for (auto& kv : t->second) {
+    const opose& P = o->mode == MODE_PCM ? kv.second.c.pose : kv.second.s.pose;
+    opose r;
+    o_pose_compose(o->d, &T, &P, &r);
+    if (keys) keys[n] = kv.first;
+    if (poses) memcpy(poses + (size_t)n * ps, r.m, sizeof(double) * ps);
+    ++n;
+  }
+  return n;
+}
 int orc_num_landmarks(void* h) { return (int)((Oracle*)h)->landmark_order.size(); }
 /* landmark l in first-seen order: key, number of observations, number of inliers */
 void orc_landmark_info(void* h, int l, uint64_t* key, int* n, int* n_inliers) {

@@ -31,6 +31,10 @@ def lib():
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_set_reference_shaped.argtypes = [C.c_void_p, C.c_int]
         L.orc_set_special_symbols.argtypes = [C.c_void_p, C.c_int, c_u8p]
+        L.orc_frame_align.restype = C.c_int
+        L.orc_frame_align.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp]
+        L.orc_robot_odom_values.restype = C.c_int
+        L.orc_robot_odom_values.argtypes = [C.c_void_p, C.c_int, c_dp, c_u64p, c_dp]
         L.orc_num_landmarks.restype = C.c_int
         L.orc_num_landmarks.argtypes = [C.c_void_p]
         L.orc_landmark_info.argtypes = [C.c_void_p, C.c_int, c_u64p, c_ip, c_ip]
@@ -344,6 +348,21 @@ class OraclePcm:
         ids = np.zeros(max(n, 1), dtype=np.int64)
         lib().orc_group_inlier_ids(self.h, g, ids.ctypes.data_as(c_llp))
         return ids[:n]
+
+    def frame_align_measurements(self, r0, ri):
+        cap = max(self.num_lc(), 1)
+        out = np.zeros((cap, psize(self.d)))
+        n = lib().orc_frame_align(self.h, ord(r0), ord(ri), dp(out))
+        return None if n < 0 else out[:n]
+
+    def robot_odom_values(self, prefix, transform=None):
+        n = lib().orc_robot_odom_values(self.h, ord(prefix), None, None, None)
+        if n < 0:
+            return None
+        keys = np.zeros(max(n, 1), dtype=np.uint64); poses = np.zeros((max(n, 1), psize(self.d)))
+        tp = dp(np.ascontiguousarray(transform, dtype=np.float64)) if transform is not None else None
+        lib().orc_robot_odom_values(self.h, ord(prefix), tp, keys.ctypes.data_as(c_u64p), dp(poses))
+        return keys[:n], poses[:n]
 
     def landmarks(self):
         """[(key, n_observations, n_inliers)] in first-seen order"""

@@ -438,3 +438,39 @@ def test_landmarks_two_robots_and_many_observations():
         o, g = run_both(3, mode, dict(params, special_symbols=('l',)), calls)
         compare_groups(o, g)
         assert len(o.landmarks()) == 2 and o.landmarks()[1][1] == 41
+
+
+def test_frame_alignment_front_half():
+    """N4: T_w0_wi measurements of the inlier inter-robot closures and getRobotOdomValues, bit-exact vs oracle."""
+    gph = synth.config4(seed=5, robots=3, P=400, n=500, outlier_frac=0.3)
+    params = dict(odom_threshold=30.0, lc_threshold=5.0)
+    o, g = run_both(3, 0, params, [(gph["odom"], gph["values"]), (gph["lcs"], [])])
+    for ri in "bc":
+        mo, mg = o.frame_align_measurements('a', ri), g.frame_align_measurements('a', ri)
+        assert mo is not None and len(mo) > 0 and np.array_equal(mo, mg), ri
+    T = orc.pose3(orc.Rz(0.3), (1.0, -2.0, 0.5))
+    ko, po = o.robot_odom_values('b', T)
+    kg, pg = g.robot_odom_values('b', T)
+    assert np.array_equal(ko, kg) and np.array_equal(po, pg) and len(ko) == 400
+    assert g.frame_align_measurements('a', 'z') is None
+
+
+def test_log_output_formats(tmp_path):
+    """N2: the status files carry the reference's headers and one row per spin (OutlierRemoval.h:54-62,
+    Pcm.h:1136-1164, RobustSolver.cpp:93-102)."""
+    gph = synth.config2(seed=4, P=300, n=60)
+    g = PcmGpu(d=3, mode=0, odom_threshold=30.0, lc_threshold=5.0)
+    g.log_output(str(tmp_path))
+    g.update(gph["odom"], gph["values"])
+    g.update(gph["lcs"], [])
+    st = open(tmp_path / "outlier_rejection_status.txt").read().splitlines()
+    assert st[0] == "total inliers spin-time mc-time" and len(st) == 3
+    tot, good = [int(v) for v in st[2].split()[:2]]
+    assert tot == g.total_lc and good == g.total_good_lc and 0 < good <= tot
+    cs = open(tmp_path / "rpgo_status.csv").read().splitlines()
+    assert cs[0] == "graph-size,spin-time(mu-s),num-lc,num-inliers" and len(cs) == 3
+    adj = np.loadtxt(tmp_path / "a-a_adj_matrix.txt")
+    n = g.group_info(0)[2]
+    assert adj.shape == (n, n) and np.array_equal(adj, adj.T)
+    assert np.array_equal(adj, g.group_adj(0, with_dist=False)[0])
+    g.close()
