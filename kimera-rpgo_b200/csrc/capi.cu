@@ -283,8 +283,8 @@ static int run_pairwise(rpgo_handle* h, Group* g, int64_t j_begin, double* dist_
     extern int g_tiled_variant_set(int);
     g_direct_minb_set(kernel == 13 ? 3 : kernel == 14 ? 4 : 2);
     if (kernel == 13 || kernel == 14) kernel = RPGO_KERNEL_DIRECT;
-    g_tiled_variant_set(kernel >= 20 && kernel <= 24 ? kernel - 20 : 4);
-    if (kernel >= 20 && kernel <= 24) kernel = RPGO_KERNEL_TILED;
+    g_tiled_variant_set(kernel >= 20 && kernel <= 35 ? kernel - 20 : 6);
+    if (kernel >= 20 && kernel <= 35) kernel = RPGO_KERNEL_TILED;
   }
   if (dist_dev) kernel = RPGO_KERNEL_DIRECT;
   if (kernel == RPGO_KERNEL_AUTO) kernel = (h->mode == MODE_PCM) ? RPGO_KERNEL_TILED : RPGO_KERNEL_DIRECT;

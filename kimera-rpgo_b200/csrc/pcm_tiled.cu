@@ -16,6 +16,7 @@
  * FP64 CUDA-core bound by design (6x6 / 3x3 fp64 with data-dependent branches: no tensor cores).
  */
 #include <cstdio>
+#include <cstdlib>
 
 #define RPGO_MATH_IMPL
 #include "kernels.cuh"
@@ -98,7 +99,7 @@ struct TiledSmem {
   static constexpr size_t JT = (size_t)RN * 32 * 8;                 /* column slab */
   static constexpr size_t IT = (size_t)2 * TILE_WARPS * RN * 8;     /* 2 stages of row records */
   static constexpr size_t SCR = (size_t)E * TILE_WARPS * 32 * 8;    /* per-thread scratch entry */
-  static constexpr size_t BYTES = JT + IT + SCR + 64;
+  static constexpr size_t BYTES = JT + IT + SCR + 256;
 };
 
 template <int D, int TILE_WARPS, int MINB, int PAIRFN>
@@ -198,6 +199,120 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, MINB)
   }
 }
 
+/* ---- phase-staggered variant --------------------------------------------------------------------------
+ * Same tiles, records and pair function; the TILE_WARPS warps of the block are split into G groups that each run their
+ * own row stream (own 2-stage TMA pipeline, own named barrier) and start a fraction of an iteration apart.  A pair check
+ * alternates between stages that saturate the FP64 pipe (H S H^T) and stages that wait on dependency chains (LLT, LU,
+ * Logmap); with every warp of a scheduler in the same stage the pipe idles through the latter.  Groups are laid out so
+ * that each scheduler (warp % 4) hosts warps of different groups. */
+template <int TW, int G>
+__device__ __forceinline__ void group_of(int w, int& grp, int& wi) {
+  if (G == 1) { grp = 0; wi = w; }
+  else if (G == 2) { grp = ((w >> 2) + (w & 3)) & 1; wi = w >> 1; }
+  else if (G == TW / 4) { grp = w >> 2; wi = w & 3; }      /* one warp of each group per scheduler */
+  else { grp = w % G; wi = w / G; }
+}
+
+template <int D, int TILE_WARPS, int G, int SEG>
+__global__ void __launch_bounds__(TILE_WARPS * 32, 1)
+    pairwise_grouped_kernel(GroupView g, const double* __restrict__ aos, const double* __restrict__ soa, int j_begin,
+                            int cb_begin, Shard sh, Thresholds th, Flagged fl, int stagger_ns) {
+  constexpr int RN = Rec<D>::N;
+  constexpr int WG = TILE_WARPS / G;
+  static_assert(WG * G == TILE_WARPS, "groups must divide the block");
+  static_assert(1 + 2 * G <= 32, "mbarrier slots");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* Jt = reinterpret_cast<double*>(smem_raw);
+  double* It = reinterpret_cast<double*>(smem_raw + TiledSmem<D, TILE_WARPS>::JT);
+  double* Scr = reinterpret_cast<double*>(smem_raw + TiledSmem<D, TILE_WARPS>::JT + TiledSmem<D, TILE_WARPS>::IT);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TiledSmem<D, TILE_WARPS>::JT + TiledSmem<D, TILE_WARPS>::IT + TiledSmem<D, TILE_WARPS>::SCR);
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  int grp, wi;
+  group_of<TILE_WARPS, G>(w, grp, wi);
+  const int cb = cb_begin + blockIdx.y;
+  const int r0 = blockIdx.x * SEG;
+  int r_end = min(g.n, cb * 32 + 31);
+  r_end = min(r_end, r0 + SEG);
+  if (r0 >= r_end) return;
+  if (sh.world > 1) {
+    const int64_t c0 = r0 / sh.chunk_rows, c1 = (r_end - 1) / sh.chunk_rows;
+    if (c0 == c1 && !row_owned_t(sh, r0)) return;
+  }
+  if (tid == 0) {
+    for (int b = 0; b < 1 + 2 * G; ++b) mbar_init(&bars[b], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], (uint32_t)TiledSmem<D, TILE_WARPS>::JT);
+    tma_load_1d(Jt, soa + (size_t)cb * RN * 32, (uint32_t)TiledSmem<D, TILE_WARPS>::JT, &bars[0]);
+  }
+  const bool leader = (wi == 0 && lane == 0);
+  double* Ig = It + (size_t)grp * 2 * WG * RN;       /* this group's two stages */
+  uint64_t* gb = bars + 1 + 2 * grp;
+  const int first = r0 + grp * WG;
+  if (leader && first < r_end) {
+    const int rows = min(WG, r_end - first);
+    mbar_expect_tx(&gb[0], (uint32_t)(rows * RN * 8));
+    tma_load_1d(Ig, aos + (size_t)first * RN, (uint32_t)(rows * RN * 8), &gb[0]);
+  }
+  mbar_wait(&bars[0], 0);
+  if (G > 1 && grp > 0 && stagger_ns > 0) __nanosleep((unsigned)(grp * stagger_ns));
+
+  const int j = cb * 32 + lane;
+  const double* Jl = Jt + lane;
+  const uint8_t pc = (uint8_t)Jl[Rec<D>::OFF_PFX * 32];
+  double* scr = Scr + tid;
+
+  int it = 0;
+  for (int base = first; base < r_end; base += TILE_WARPS, ++it) {
+    const int stage = it & 1;
+    if (leader && base + TILE_WARPS < r_end) {
+      const int rows = min(WG, r_end - (base + TILE_WARPS));
+      mbar_expect_tx(&gb[stage ^ 1], (uint32_t)(rows * RN * 8));
+      tma_load_1d(Ig + (size_t)(stage ^ 1) * WG * RN, aos + (size_t)(base + TILE_WARPS) * RN, (uint32_t)(rows * RN * 8),
+                  &gb[stage ^ 1]);
+    }
+    mbar_wait(&gb[stage], (uint32_t)((it >> 1) & 1));
+    const int i = base + wi;
+    if (i < r_end && row_owned_t(sh, i)) {
+      const double* Ir = Ig + ((size_t)stage * WG + wi) * RN;
+      bool ok = false;
+      if (j < g.n && j > i && j >= j_begin) {
+        const uint8_t pa = (uint8_t)Ir[Rec<D>::OFF_PFX];
+        const double* Tc = (pa != pc) ? Jl + Rec<D>::OFF_TB * 32 : Jl + Rec<D>::OFF_TF * 32;
+        const double* Td = (pa != pc) ? Jl + Rec<D>::OFF_TF * 32 : Jl + Rec<D>::OFF_TB * 32;
+        double dist;
+        bool near, bad;
+        ok = pair_check_v2<D>(Ir + Rec<D>::OFF_TF, 1, Ir + Rec<D>::OFF_TB, 1, Ir + Rec<D>::OFF_LC, 1, Tc, 32, Td, 32,
+                              Jl + Rec<D>::OFF_LC * 32, 32, scr, TILE_WARPS * 32, th, &dist, &near, &bad);
+        if (bad)
+          ok = pair_check_exact<D>(Ir + Rec<D>::OFF_TF, 1, Ir + Rec<D>::OFF_TB, 1, Ir + Rec<D>::OFF_LC, 1, Tc, 32, Td, 32,
+                                   Jl + Rec<D>::OFF_LC * 32, 32, scr, TILE_WARPS * 32, &th, &dist, &near);
+        if (near) {
+          const unsigned long long slot = atomicAdd(fl.count, 1ULL);
+          if ((int64_t)slot < fl.cap) {
+            fl.pairs[2 * slot] = i;
+            fl.pairs[2 * slot + 1] = j;
+          }
+        }
+      }
+      const unsigned word = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) {
+        unsigned keep = 0;
+        if (j_begin > cb * 32) keep = (j_begin >= cb * 32 + 32) ? 0xffffffffu : ((1u << (j_begin - cb * 32)) - 1u);
+        uint32_t* p = g.bits + (size_t)i * g.stride32 + cb;
+        *p = (*p & keep) | word;
+      }
+    }
+    if (G == 1) __syncthreads();
+    else if (WG == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(WG * 32) : "memory");
+  }
+}
+
 static void gather_launch(int dim, GroupView g, const double* traj, int k0, double* aos, double* soa, cudaStream_t st) {
   if (k0 >= g.n) return;
   if (dim == 3) gather_records_kernel<3><<<g.n - k0, 160, 0, st>>>(g, traj, k0, aos, soa);
@@ -260,7 +375,7 @@ int fastmath_check(long long n, unsigned long long seed, unsigned long long* mis
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
-int g_tiled_variant = 4; /* 4 = 12 warps x 1 block/SM, straight-line pair function (default); 2 = same with pair_check_v1; experiment knobs: 0 = 4 warps x 2 blocks, 1 = 10 x 1, 3 = 8 x 1 */
+int g_tiled_variant = 6; /* 6 = 12 warps x 1 block/SM in 3 phase-shifted groups, straight-line pair function (default); 4 = same, one group; 2 = same with pair_check_v1; experiment knobs: 0 = 4 warps x 2 blocks, 1 = 10 x 1, 3 = 8 x 1 */
 
 template <int D, int TW, int MINB, int PAIRFN>
 static void launch_variant(GroupView g, const double* aos, const double* soa, int j_begin, int cb_begin, dim3 grid, Shard sh,
@@ -274,6 +389,25 @@ static void launch_variant(GroupView g, const double* aos, const double* soa, in
   pairwise_tiled_kernel<D, TW, MINB, PAIRFN><<<grid, TW * 32, TiledSmem<D, TW>::BYTES, st>>>(g, aos, soa, j_begin, cb_begin, sh, th, fl);
 }
 
+int g_stagger_ns = -1;
+template <int D, int TW, int G, int SEG>
+static void launch_grouped(GroupView g, const double* aos, const double* soa, int j_begin, int cb_begin, int cb_end, Shard sh,
+                           Thresholds th, Flagged fl, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(pairwise_grouped_kernel<D, TW, G, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)TiledSmem<D, TW>::BYTES);
+    attr = true;
+  }
+  if (g_stagger_ns < 0) {
+    const char* e = getenv("RPGO_STAGGER_NS");
+    g_stagger_ns = e ? atoi(e) : 0; /* measured: the groups drift apart on their own */
+  }
+  dim3 grid((g.n + SEG - 1) / SEG, cb_end - cb_begin);
+  pairwise_grouped_kernel<D, TW, G, SEG><<<grid, TW * 32, TiledSmem<D, TW>::BYTES, st>>>(g, aos, soa, j_begin, cb_begin, sh, th, fl,
+                                                                                           g_stagger_ns);
+}
+
 void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, const double* soa, int j_begin, Shard sh,
                            Thresholds th, Flagged fl, cudaStream_t st) {
   (void)mode; /* MODE_PCM only */
@@ -281,6 +415,18 @@ void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, co
   const int cb_begin = j_begin / 32;
   const int cb_end = (g.n + 31) / 32;
   dim3 grid((g.n + TILE_SEG - 1) / TILE_SEG, cb_end - cb_begin);
+  if (dim == 3 && g_tiled_variant >= 5) {
+    switch (g_tiled_variant) {
+      case 5: launch_grouped<3, 12, 2, 512>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); break;
+      case 6: launch_grouped<3, 12, 3, 512>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); break;
+      case 7: launch_grouped<3, 12, 3, 1024>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); break;
+      case 10: launch_grouped<3, 12, 6, 512>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); break;
+      case 11: launch_grouped<3, 12, 12, 512>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); break;
+      case 8: launch_grouped<3, 12, 4, 512>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); break;
+      default: launch_grouped<3, 12, 1, 512>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); break;
+    }
+    return;
+  }
   if (dim == 3) {
     switch (g_tiled_variant) {
       case 1: launch_variant<3, 10, 1, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st); break;
@@ -290,7 +436,8 @@ void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, co
       default: launch_variant<3, 12, 1, 2>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st); break;
     }
   } else {
-    if (g_tiled_variant == 2) launch_variant<2, 12, 1, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st);
+    if (g_tiled_variant >= 5) launch_grouped<2, 12, 3, 512>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st);
+    else if (g_tiled_variant == 2) launch_variant<2, 12, 1, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st);
     else launch_variant<2, 12, 1, 2>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st);
   }
 }
