@@ -144,6 +144,22 @@ int rpgo_lc_remove_last(rpgo_handle* h, int32_t g, uint64_t* key_from, uint64_t*
 int rpgo_find_inliers(rpgo_handle* h, int32_t g, int32_t clique_mode, int64_t n_new, int64_t prev_size,
                       int32_t* ids_out, int64_t* size_out, int32_t* true_clique_out);
 
+/* ---- multi-GPU inlier selection: candidate partition + incumbent exchange ------------------------------
+ * With cfg.world > 1 and an exchange function registered, rpgo_find_inliers partitions the clique search's root
+ * candidates over the ranks (candidate v belongs to rank v mod world in the heuristic, root n-1-v likewise in the
+ * exact search) and calls `fn` on the host, on every rank in the same order, to combine the incumbent:
+ *   RPGO_XCHG_MIN_I64 / RPGO_XCHG_MAX_I64: in-place all-reduce of count int64 values in buf;
+ *   RPGO_XCHG_BCAST_I32: broadcast count int32 values in buf from rank `root`.
+ * fn returns 0 on success.  The library stays free of a communication dependency: the caller implements fn with
+ * whatever it already uses (the Python harness: torch.distributed over NCCL/NVLink).  Without a registered
+ * function every rank searches all candidates (replicated, same result).  The reference has no counterpart:
+ * its clique search is single-threaded (GraphUtils.cpp:9-44). */
+#define RPGO_XCHG_MIN_I64 0
+#define RPGO_XCHG_MAX_I64 1
+#define RPGO_XCHG_BCAST_I32 2
+typedef int (*rpgo_exchange_fn)(void* user, int32_t op, void* buf, int64_t count, int32_t root);
+int rpgo_set_exchange(rpgo_handle* h, rpgo_exchange_fn fn, void* user);
+
 /* ---- N4: multi-robot frame alignment, the batched front half (Pcm::multirobotValueInitialization,
  * Pcm.h:1024-1055; the GNC pose averaging that follows stays on GTSAM) -------------------------------------
  * For the m closures closure_idx[] of group g (normally its inliers) writes T_w0_wi = T_w0_front . T_front_back .

@@ -43,6 +43,7 @@ SYMBOLS = [
     ("rpgo_find_group", C.c_int32, [C.c_void_p, C.c_uint8, C.c_uint8]),
     ("rpgo_lc_remove_last", C.c_int, [C.c_void_p, C.c_int32, c_u64p, c_u64p]),
     ("rpgo_find_inliers", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, c_i32p, c_i64p, c_i32p]),
+    ("rpgo_set_exchange", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("rpgo_frame_align_measurements", C.c_int, [C.c_void_p, C.c_int32, C.c_uint8, C.c_int64, c_i32p, c_dp]),
     ("rpgo_robot_odom_values", C.c_int, [C.c_void_p, C.c_uint8, c_dp, C.c_int64, c_u64p, c_dp, c_i64p]),
     ("rpgo_adj_bits", C.c_int, [C.c_void_p, C.c_int32, c_u64p, C.c_int64]),
@@ -60,6 +61,9 @@ SYMBOLS = [
     ("rpgo_debug_check_fastmath", C.c_int, [C.c_int64, C.c_uint64, c_u64p, c_u64p]),
     ("rpgo_version", C.c_char_p, []),
 ]
+
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32)
+XCHG_MIN_I64, XCHG_MAX_I64, XCHG_BCAST_I32 = 0, 1, 2
 
 _lib = None
 

@@ -139,6 +139,8 @@ struct rpgo_handle {
   cudaStream_t stream = nullptr;
   std::string err;
   int64_t launches = 0;
+  rpgo_exchange_fn xchg = nullptr; /* incumbent exchange of the sharded clique searches */
+  void* xchg_user = nullptr;
 
   /* trajectory table: entry 0 is the default-constructed T (identity, zero covariance, node 0) */
   DevBuf traj;
@@ -933,24 +935,36 @@ int rpgo_find_inliers(rpgo_handle* h, int32_t gi, int32_t clique_mode, int64_t n
   s.rwork = h->c_rwork.as<uint32_t>();
   s.rwork_blocks = blocks;
   int r;
+  CliqueShard cs;
+  cs.rank = h->cfg.rank;
+  cs.world = h->cfg.world;
+  cs.exchange = h->xchg;
+  cs.user = h->xchg_user;
   if (clique_mode == RPGO_CLIQUE_HEU) {
     r = clique_heuristic(g->bits.as<uint32_t>(), g->stride32, n, g->deg.as<int32_t>(), 0, -1, s, ids_out, true_clique_out,
-                         &h->launches, st);
+                         &h->launches, st, cs);
     if (r < -1) { h->err = "clique_heuristic failed: " + std::to_string(r); return RPGO_ERR_CUDA; }
     *size_out = r;
   } else if (clique_mode == RPGO_CLIQUE_HEU_INCREMENTAL) {
     if (n_new < 0 || n_new > n || prev_size < 0) return RPGO_ERR_INVALID;
     r = clique_heuristic(g->bits.as<uint32_t>(), g->stride32, n, g->deg.as<int32_t>(), (int)(n - n_new), (int)prev_size, s,
-                         ids_out, true_clique_out, &h->launches, st);
+                         ids_out, true_clique_out, &h->launches, st, cs);
     if (r < -1) { h->err = "clique_heuristic failed: " + std::to_string(r); return RPGO_ERR_CUDA; }
     *size_out = (r > prev_size) ? r : 0; /* GraphUtils.cpp:40-43 */
   } else if (clique_mode == RPGO_CLIQUE_EXACT) {
-    r = clique_exact(g->bits.as<uint32_t>(), g->stride32, n, g->deg.as<int32_t>(), s, ids_out, &h->launches, st);
+    r = clique_exact(g->bits.as<uint32_t>(), g->stride32, n, g->deg.as<int32_t>(), s, ids_out, &h->launches, st, cs);
     if (r < 0) { h->err = "clique_exact failed: " + std::to_string(r); return RPGO_ERR_CUDA; }
     *size_out = r;
   } else {
     return RPGO_ERR_INVALID;
   }
+  return RPGO_OK;
+}
+
+int rpgo_set_exchange(rpgo_handle* h, rpgo_exchange_fn fn, void* user) {
+  if (!h) return RPGO_ERR_INVALID;
+  h->xchg = fn;
+  h->xchg_user = user;
   return RPGO_OK;
 }
 

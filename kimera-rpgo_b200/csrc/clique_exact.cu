@@ -48,7 +48,8 @@ __device__ __forceinline__ void ex_block_sum_max(int& s, int& m, int* sh) {
 __global__ void __launch_bounds__(EX_THREADS) exact_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n,
                                                            const int32_t* __restrict__ deg, unsigned long long* incumbent,
                                                            uint32_t* stacks, int depth_max, int32_t* paths,
-                                                           int32_t* best_paths, unsigned long long* best_keys) {
+                                                           int32_t* best_paths, unsigned long long* best_keys, int rank,
+                                                           int world) {
   __shared__ int sh[64];
   __shared__ unsigned long long s_inc;
   const int W = (n + 31) / 32;
@@ -59,7 +60,9 @@ __global__ void __launch_bounds__(EX_THREADS) exact_kernel(const uint32_t* __res
   (void)cnts;
   int32_t* best = best_paths + (size_t)blockIdx.x * (depth_max + 2);
 
-  for (int root = n - 1 - (int)blockIdx.x; root >= 0; root -= gridDim.x) {
+  /* roots n-1-rank, n-1-rank-world, ...: this rank's share (world = 1: all of them) */
+  for (long long rr = (long long)n - 1 - rank - (long long)blockIdx.x * world; rr >= 0; rr -= (long long)gridDim.x * world) {
+    const int root = (int)rr;
     __syncthreads();
     if (tid == 0) s_inc = *(volatile unsigned long long*)incumbent;
     __syncthreads();
@@ -171,8 +174,10 @@ __global__ void __launch_bounds__(EX_THREADS) exact_kernel(const uint32_t* __res
   } while (0)
 
 int clique_exact(const uint32_t* bits, int64_t stride32, int n, const int32_t* deg, CliqueScratch s, int32_t* ids_out_host,
-                 int64_t* launches, cudaStream_t st) {
+                 int64_t* launches, cudaStream_t st, CliqueShard cs) {
   (void)s;
+  const bool sharded = cs.world > 1 && cs.exchange != nullptr;
+  const int world = sharded ? cs.world : 1, rank = sharded ? cs.rank : 0;
   if (n <= 0) return 0;
   const int W = (n + 31) / 32;
   std::vector<int32_t> hdeg(n);
@@ -186,7 +191,8 @@ int clique_exact(const uint32_t* bits, int64_t stride32, int n, const int32_t* d
   const size_t budget = (size_t)8 << 30;
   if ((size_t)grid * per_block > budget) grid = (int)(budget / per_block);
   if (grid < 1) return -4; /* graph too large for the exact search's stack budget */
-  if (grid > n) grid = n;
+  if (grid > (n + world - 1) / world) grid = (n + world - 1) / world;
+  if (grid < 1) grid = 1;
   uint32_t* stacks = nullptr;
   int32_t *paths = nullptr, *best = nullptr;
   unsigned long long *inc = nullptr, *keys = nullptr;
@@ -197,20 +203,32 @@ int clique_exact(const uint32_t* bits, int64_t stride32, int n, const int32_t* d
   EXCHECK(cudaMalloc(&keys, (size_t)grid * sizeof(unsigned long long)));
   EXCHECK(cudaMemsetAsync(inc, 0, sizeof(unsigned long long), st));
   EXCHECK(cudaMemsetAsync(keys, 0, (size_t)grid * sizeof(unsigned long long), st));
-  exact_kernel<<<grid, EX_THREADS, 0, st>>>(bits, stride32, n, deg, inc, stacks, depth_max, paths, best, keys);
+  exact_kernel<<<grid, EX_THREADS, 0, st>>>(bits, stride32, n, deg, inc, stacks, depth_max, paths, best, keys, rank, world);
   *launches += 1;
   unsigned long long hinc = 0;
   EXCHECK(cudaMemcpyAsync(&hinc, inc, sizeof(hinc), cudaMemcpyDeviceToHost, st));
   EXCHECK(cudaStreamSynchronize(st));
   EXCHECK(cudaGetLastError());
+  int xrc = 0;
+  const unsigned long long mine = hinc;
+  if (sharded) {
+    /* incumbent all-reduce: larger size, then larger root — the reference's preference between roots */
+    long long key = (long long)hinc;
+    xrc = cs.exchange(cs.user, RPGO_XCHG_MAX_I64, &key, 1, 0);
+    hinc = (unsigned long long)key;
+  }
   const int size = (int)(hinc >> 32), root = (int)(hinc & 0xffffffffu);
-  int rc = size;
-  if (size > 0) {
-    const int b = (n - 1 - root) % grid;
-    std::vector<int32_t> p(size);
-    EXCHECK(cudaMemcpy(p.data(), best + (size_t)b * (depth_max + 2), sizeof(int32_t) * size, cudaMemcpyDeviceToHost));
-    /* the reference returns the clique in ascending id order (ids pushed while unwinding) */
-    for (int l = 0; l < size; ++l) ids_out_host[l] = p[size - 1 - l];
+  int rc = xrc != 0 ? -3 : size;
+  if (size > 0 && xrc == 0) {
+    const int owner = (n - 1 - root) % world;
+    if (owner == rank && mine == hinc) {
+      const int b = ((n - 1 - root - rank) / world) % grid;
+      std::vector<int32_t> p(size);
+      EXCHECK(cudaMemcpy(p.data(), best + (size_t)b * (depth_max + 2), sizeof(int32_t) * size, cudaMemcpyDeviceToHost));
+      /* the reference returns the clique in ascending id order (ids pushed while unwinding) */
+      for (int l = 0; l < size; ++l) ids_out_host[l] = p[size - 1 - l];
+    }
+    if (sharded && cs.exchange(cs.user, RPGO_XCHG_BCAST_I32, ids_out_host, size, owner) != 0) rc = -3;
   }
   cudaFree(stacks);
   cudaFree(paths);

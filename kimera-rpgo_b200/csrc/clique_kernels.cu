@@ -25,6 +25,7 @@
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
+#include <ctime>
 #include <vector>
 
 #include "kernels.cuh"
@@ -186,8 +187,8 @@ __global__ void undead_kernel(const uint32_t* __restrict__ bits, int64_t stride3
  *         (ULLONG_MAX = none).  picks_block: per-block pick log (n ints each). */
 __global__ void __launch_bounds__(HEU_THREADS) heu_round_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n,
                                                                 const int32_t* __restrict__ deg,
-                                                                const uint32_t* __restrict__ degmask, int first, int M,
-                                                                unsigned long long* ctl, int32_t* picks_block,
+                                                                const uint32_t* __restrict__ degmask, int first, int vstep,
+                                                                int M, unsigned long long* ctl, int32_t* picks_block,
                                                                 int32_t* dead_flags) {
   extern __shared__ uint32_t R[];
   __shared__ int sh[64];
@@ -197,7 +198,9 @@ __global__ void __launch_bounds__(HEU_THREADS) heu_round_kernel(const uint32_t* 
   const int tid = threadIdx.x;
   int32_t* my_picks = picks_block + (size_t)blockIdx.x * n;
 
-  for (int v = first + blockIdx.x; v < n; v += gridDim.x) {
+  /* candidates first, first + vstep, ...: vstep > 1 when the candidates are partitioned over ranks */
+  for (long long vv = first + (long long)blockIdx.x * vstep; vv < n; vv += (long long)gridDim.x * vstep) {
+    const int v = (int)vv;
     /* a lower-index candidate already improved: everything from here on is re-evaluated next round */
     __syncthreads();
     if (tid == 0) s_abort = ((long long)(*(volatile unsigned long long*)ctl >> 32) < (long long)v) ? 1 : 0;
@@ -402,7 +405,9 @@ __global__ void heu_select_kernel(int n, int K, const int32_t* __restrict__ elim
  * entries of the reference's returned buffer; true_out_host (optional) the greedy clique itself. */
 int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_t* deg, int first, int maxclq0,
                      CliqueScratch s, int32_t* ids_out_host, int32_t* true_out_host, int64_t* launches,
-                     cudaStream_t st) {
+                     cudaStream_t st, CliqueShard cs) {
+  const bool sharded = cs.world > 1 && cs.exchange != nullptr;
+  const int world = sharded ? cs.world : 1, rank = sharded ? cs.rank : 0;
   if (n <= 0) return -1;
   const int W = (n + 31) / 32;
   const size_t smem = (size_t)W * sizeof(uint32_t);
@@ -415,33 +420,56 @@ int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_
   /* "dead" cache: a candidate that could not beat bound M cannot beat any M' >= M as long as its filtered
    * neighbourhood {u : deg(u) >= M} is unchanged, i.e. as long as no vertex has M <= deg < M'.  The host checks
    * that on the sorted degree list at every bound change and clears the cache otherwise. */
+  const bool trace = getenv("RPGO_CLIQUE_TRACE") != nullptr;
+  auto now_ms = []() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  };
+  const double t_begin = now_ms();
+  double t_round0 = 0;
   std::vector<int32_t> hdeg(n);
   CUCHECK(cudaMemcpyAsync(hdeg.data(), deg, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
   CUCHECK(cudaMemsetAsync(s.elim, 0, sizeof(int32_t) * n, st));
   CUCHECK(cudaStreamSynchronize(st));
-  /* vertices sorted by degree, for the "whose filter membership changes between M and M'" query */
-  std::vector<int32_t> by_deg(n);
-  for (int i = 0; i < n; ++i) by_deg[i] = i;
-  std::sort(by_deg.begin(), by_deg.end(), [&](int a, int b) { return hdeg[a] < hdeg[b]; });
+  std::vector<int32_t> changed; /* vertices whose filter membership changes between two bounds */
   int M = maxclq0;
   int winner = -1, winner_M = 0, winner_icc = 0, winner_block = 0;
+  bool winner_local = true;
   int start = first < 0 ? 0 : first;
   std::vector<int32_t> picks_host;
   const int grid_cap = (int)s.rwork_blocks;
   unsigned long long h_ctl;
+  if (trace) fprintf(stderr, "[clique] setup (degree copy + sort) %.3f ms\n", now_ms() - t_begin);
   while (start < n) {
+    t_round0 = now_ms();
     const unsigned long long none = ~0ULL;
     const unsigned long long init3[3] = {none, 0ULL, 0ULL};
     CUCHECK(cudaMemcpyAsync(s.ctl, init3, sizeof(init3), cudaMemcpyHostToDevice, st));
     degmask_kernel<<<(W + 127) / 128, 128, 0, st>>>(deg, n, M, s.degmask, W);
-    int grid = n - start;
+    /* candidates of this rank: v = start (mod nothing) for one GPU, v = rank (mod world) when partitioned */
+    const int v0 = start + (((rank - start) % world) + world) % world;
+    int grid = (n - v0 + world - 1) / world;
     if (grid > grid_cap) grid = grid_cap;
-    heu_round_kernel<<<grid, HEU_THREADS, smem, st>>>(bits, stride32, n, deg, s.degmask, start, M,
-                                                      (unsigned long long*)s.ctl, (int32_t*)s.rwork, s.elim);
-    *launches += 2;
+    if (grid > 0) {
+      heu_round_kernel<<<grid, HEU_THREADS, smem, st>>>(bits, stride32, n, deg, s.degmask, v0, world, M,
+                                                        (unsigned long long*)s.ctl, (int32_t*)s.rwork, s.elim);
+      *launches += 1;
+    }
+    *launches += 1;
     CUCHECK(cudaMemcpyAsync(&h_ctl, s.ctl, sizeof(h_ctl), cudaMemcpyDeviceToHost, st));
     CUCHECK(cudaStreamSynchronize(st));
-    if (getenv("RPGO_CLIQUE_TRACE")) {
+    bool local_winner = true;
+    if (sharded) {
+      /* incumbent exchange: the lowest-index improving candidate over all ranks wins the round */
+      const unsigned long long mine = h_ctl;
+      long long key = (h_ctl == none) ? LLONG_MAX : (long long)h_ctl;
+      if (cs.exchange(cs.user, RPGO_XCHG_MIN_I64, &key, 1, 0) != 0) return -3;
+      h_ctl = (key == LLONG_MAX) ? none : (unsigned long long)key;
+      local_winner = (h_ctl == mine);
+    }
+    if (trace) {
+      fprintf(stderr, "[clique] rank %d round kernel+sync %.3f ms\n", rank, now_ms() - t_round0);
       unsigned long long c[3];
       cudaMemcpy(c, s.ctl, sizeof(c), cudaMemcpyDeviceToHost);
       fprintf(stderr, "[clique] round start=%d M=%d grid=%d -> improver=%lld icc=%d | chains started %llu, windows %llu\n", start, M, grid,
@@ -451,20 +479,25 @@ int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_
     winner = (int)(h_ctl >> 32);
     winner_icc = (int)(h_ctl & 0xffffffffu);
     winner_M = M;
-    winner_block = (winner - start) % grid;
-    /* keep the winner's pick log (its block may be reused next round) */
-    CUCHECK(cudaMemcpyAsync(s.picks, (int32_t*)s.rwork + (size_t)winner_block * n,
-                            sizeof(int32_t) * (size_t)(winner_icc - 1 > 0 ? winner_icc - 1 : 0), cudaMemcpyDeviceToDevice, st));
+    winner_local = local_winner;
+    if (local_winner) {
+      winner_block = ((winner - v0) / world) % grid;
+      /* keep the winner's pick log (its block may be reused next round) */
+      CUCHECK(cudaMemcpyAsync(s.picks, (int32_t*)s.rwork + (size_t)winner_block * n,
+                              sizeof(int32_t) * (size_t)(winner_icc - 1 > 0 ? winner_icc - 1 : 0), cudaMemcpyDeviceToDevice, st));
+    }
     {
       /* any vertex with M <= deg < winner_icc changes the filter: cached verdicts are no longer valid */
-      auto lo = std::lower_bound(by_deg.begin(), by_deg.end(), M, [&](int a, int val) { return hdeg[a] < val; });
-      auto hi = std::lower_bound(by_deg.begin(), by_deg.end(), winner_icc, [&](int a, int val) { return hdeg[a] < val; });
-      const int nx = (int)(hi - lo);
+      changed.clear();
+      for (int u = 0; u < n && changed.size() <= 4096; ++u)
+        if (hdeg[u] >= M && hdeg[u] < winner_icc) changed.push_back(u);
+      const int nx = (int)changed.size();
       if (nx > 4096) {
         CUCHECK(cudaMemsetAsync(s.elim, 0, sizeof(int32_t) * n, st));
       } else if (nx > 0) {
         /* only candidates adjacent to one of those vertices see a different filtered neighbourhood */
-        CUCHECK(cudaMemcpyAsync(s.result, &*lo, sizeof(int32_t) * nx, cudaMemcpyHostToDevice, st));
+        CUCHECK(cudaMemcpyAsync(s.result, changed.data(), sizeof(int32_t) * nx, cudaMemcpyHostToDevice, st));
+        CUCHECK(cudaStreamSynchronize(st)); /* `changed` is reused next round */
         undead_kernel<<<nx, 128, 0, st>>>(bits, stride32, n, s.result, nx, s.elim);
         *launches += 1;
       }
@@ -473,8 +506,22 @@ int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_
     start = winner + 1;
   }
   if (winner < 0) return M; /* no candidate improved on maxclq0 (incremental mode) */
+  const double t_replay = now_ms();
+  if (trace) fprintf(stderr, "[clique] rounds done at %.3f ms\n", t_replay - t_begin);
 
   const int K = winner_icc - 1;
+  if (!winner_local) {
+    /* the final winning chain ran on another rank: replay that one candidate here (same bound, same filter) to get
+     * its pick log; intermediate winners only moved the bound and need no log */
+    const unsigned long long init3[3] = {~0ULL, 0ULL, 0ULL};
+    CUCHECK(cudaMemcpyAsync(s.ctl, init3, sizeof(init3), cudaMemcpyHostToDevice, st));
+    CUCHECK(cudaMemsetAsync(s.elim + winner, 0, sizeof(int32_t), st));
+    degmask_kernel<<<(W + 127) / 128, 128, 0, st>>>(deg, n, winner_M, s.degmask, W);
+    heu_round_kernel<<<1, HEU_THREADS, smem, st>>>(bits, stride32, n, deg, s.degmask, winner, n, winner_M,
+                                                   (unsigned long long*)s.ctl, (int32_t*)s.rwork, s.elim);
+    *launches += 2;
+    CUCHECK(cudaMemcpyAsync(s.picks, (int32_t*)s.rwork, sizeof(int32_t) * (size_t)(K > 0 ? K : 0), cudaMemcpyDeviceToDevice, st));
+  }
   picks_host.resize(K > 0 ? K : 1);
   if (K > 0) CUCHECK(cudaMemcpyAsync(picks_host.data(), s.picks, sizeof(int32_t) * K, cudaMemcpyDeviceToHost, st));
   CUCHECK(cudaStreamSynchronize(st));
@@ -528,6 +575,7 @@ int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_
   *launches += 1;
   CUCHECK(cudaMemcpyAsync(ids_out_host + 1, s.result + 1, sizeof(int32_t) * K, cudaMemcpyDeviceToHost, st));
   CUCHECK(cudaStreamSynchronize(st));
+  if (trace) fprintf(stderr, "[clique] replay %.3f ms, total %.3f ms\n", now_ms() - t_replay, now_ms() - t_begin);
   return M;
 }
 

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "rpgo_math.cuh"
+#include "../../include/rpgo_b200.h"
 
 namespace rpgo {
 
@@ -85,11 +86,18 @@ struct CliqueScratch {
   uint32_t* rwork;          /* per-block working sets: grid x stride32 */
   int64_t rwork_blocks;
 };
+/* candidate partition of the clique searches over ranks; exchange is the host-provided collective
+ * (rpgo_set_exchange): op RPGO_XCHG_*, in place on buf */
+struct CliqueShard {
+  int rank = 0, world = 1;
+  int (*exchange)(void* user, int32_t op, void* buf, int64_t count, int32_t root) = nullptr;
+  void* user = nullptr;
+};
 int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_t* deg, int first, int maxclq0,
                      CliqueScratch s, int32_t* ids_out_host, int32_t* true_out_host, int64_t* launches,
-                     cudaStream_t st);
+                     cudaStream_t st, CliqueShard cs = CliqueShard());
 int clique_exact(const uint32_t* bits, int64_t stride32, int n, const int32_t* deg, CliqueScratch s,
-                 int32_t* ids_out_host, int64_t* launches, cudaStream_t st);
+                 int32_t* ids_out_host, int64_t* launches, cudaStream_t st, CliqueShard cs = CliqueShard());
 
 double fp64_peak_tflops(cudaStream_t st);
 int fastmath_check(long long n, unsigned long long seed, unsigned long long* mismatches, unsigned long long* checked,

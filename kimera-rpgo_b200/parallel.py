@@ -49,3 +49,56 @@ def allgather_adjacency(pcm, g, device, group=None):
         with torch.cuda.stream(st):
             exchange_row_chunks(t, pcm.cfg.rank, world, chunk_rows, group=group)
     pcm.finalize(g)
+
+
+def make_exchange(device=None, group=None):
+    """Host collective for the sharded clique searches (rpgo_set_exchange): all-reduce MIN/MAX of int64 and
+    broadcast of int32 over torch.distributed — NCCL (device tensors, NVLink) when `device` is a CUDA device,
+    the process group's CPU backend otherwise (gloo in the tests).  Returns the ctypes callback; the caller must
+    keep a reference to it for as long as it is registered."""
+    import ctypes as C
+
+    import numpy as np
+
+    from . import _capi
+
+    state = {}
+
+    def staging(dtype, count):
+        key = (dtype, count)
+        if key not in state:
+            state[key] = (torch.empty(count, dtype=dtype, pin_memory=True), torch.empty(count, dtype=dtype, device=device))
+        return state[key]
+
+    def fn(_user, op, buf, count, root):
+        try:
+            if op == _capi.XCHG_BCAST_I32:
+                arr = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_int32)), shape=(count,))
+            else:
+                arr = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_int64)), shape=(count,))
+            t = torch.from_numpy(arr)
+            if device is not None:
+                pin, td = staging(t.dtype, count)
+                pin.copy_(t)
+                td.copy_(pin, non_blocking=True)
+            else:
+                td = t
+            if op == _capi.XCHG_MIN_I64:
+                dist.all_reduce(td, op=dist.ReduceOp.MIN, group=group)
+            elif op == _capi.XCHG_MAX_I64:
+                dist.all_reduce(td, op=dist.ReduceOp.MAX, group=group)
+            elif op == _capi.XCHG_BCAST_I32:
+                dist.broadcast(td, src=root if group is None else dist.get_global_rank(group, root), group=group)
+            else:
+                return 2
+            if device is not None:
+                pin.copy_(td, non_blocking=True)
+                torch.cuda.current_stream(device).synchronize()
+                t.copy_(pin)
+            return 0
+        except Exception as e:  # never unwind through the C frame
+            import sys
+            print("rpgo exchange callback failed: %r" % (e,), file=sys.stderr)
+            return 1
+
+    return _capi.EXCHANGE_FN(fn)

@@ -56,6 +56,15 @@ class PcmGpu:
             raise RpgoError("rpgo_create failed with status %d (no usable CUDA device? there is no CPU fallback)" % rc)
         self.d, self.mode = d, mode
         self.auto_exchange = True
+        self._exchange_cb = None
+        if world > 1:
+            # sharded clique searches: register the incumbent exchange when a process group is up
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() == world:
+                import torch
+                from . import parallel
+                dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else None
+                self.set_exchange(parallel.make_exchange(dev))
         self.ps = 12 if d == 3 else 4
         self.n = 6 if d == 3 else 3
         self.incremental = bool(incremental)
@@ -103,6 +112,12 @@ class PcmGpu:
             f.write("%d %d %d %d\n" % (self.total_lc, self.total_good_lc, int(spin_s * 1e3), int(clique_s * 1e3)))
         with open(os.path.join(folder, "rpgo_status.csv"), "a") as f:  # RobustSolver::update
             f.write("%d,%d,%d,%d\n" % (len(self.output), int(spin_s * 1e6), self.total_lc, self.total_good_lc))
+
+    def set_exchange(self, cb):
+        """Register (or clear, cb=None) the collective the sharded clique searches call; see rpgo_set_exchange."""
+        self._exchange_cb = cb  # keep the ctypes thunk alive
+        self._check(self.lib.rpgo_set_exchange(self.h, C.cast(cb, C.c_void_p) if cb is not None else None, None),
+                    "rpgo_set_exchange")
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h:

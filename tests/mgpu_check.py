@@ -43,6 +43,29 @@ def main():
         if rank == 0:
             print("%s: %d groups, %d closures, %d inliers: %s" % (name, len(single.groups()), single.num_lc(),
                                                                    single.num_inliers(), "OK" if ok else "FAIL"))
+    # rank-partitioned clique searches (heuristic, incremental, exact) with the NCCL incumbent exchange
+    pkg = sys.modules[PcmGpu.__module__.rsplit(".", 1)[0]]
+    rng = np.random.default_rng(77)
+    single = PcmGpu(3, 0, device=local)
+    shard = PcmGpu(3, 0, device=local, rank=rank, world=world)
+    assert shard._exchange_cb is not None
+    for t_ in range(12):
+        n = int(rng.integers(2, 120))
+        p = rng.uniform(0.1, 0.9)
+        a = np.triu((rng.random((n, n)) < p).astype(np.uint8), 1)
+        a = a + a.T
+        modes = [(pkg.CLIQUE_HEU, 0, 0), (pkg.CLIQUE_HEU_INCREMENTAL, int(rng.integers(1, n)), int(rng.integers(0, 5)))]
+        if n <= 80 and p <= 0.8:
+            modes.append((pkg.CLIQUE_EXACT, 0, 0))
+        g1, g2 = single.load_adjacency(a), shard.load_adjacency(a)
+        for m, nn, pv in modes:
+            k1, i1, _ = single.find_inliers_raw(g1, m, nn, pv)
+            k2, i2, _ = shard.find_inliers_raw(g2, m, nn, pv)
+            if k1 != k2 or i1.tolist() != i2.tolist():
+                ok = False
+                print("rank %d CLIQUE MISMATCH case %d mode %d: %d vs %d" % (rank, t_, m, k1, k2))
+    if rank == 0:
+        print("sharded clique searches: %s" % ("OK" if ok else "FAIL"))
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

@@ -474,3 +474,64 @@ def test_log_output_formats(tmp_path):
     assert adj.shape == (n, n) and np.array_equal(adj, adj.T)
     assert np.array_equal(adj, g.group_adj(0, with_dist=False)[0])
     g.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_clique_searches_match_single(world):
+    """Candidates / roots partitioned over `world` ranks with the incumbent exchanged through rpgo_set_exchange:
+    every rank must return exactly what one GPU returns (size, scratch-buffer ids, true clique; exact: same ids)."""
+    from gpu_common import run_sharded
+    rng = np.random.default_rng(31)
+    cases = []
+    for t in range(24):
+        n = int(rng.integers(2, 160))
+        p = rng.uniform(0.1, 0.95)
+        cases.append((rand_graph(rng, n, p), int(rng.integers(1, n)), int(rng.integers(0, 6)), n <= 90 and p <= 0.8))
+    single = PcmGpu(3, 0)
+    want = []
+    for a, num_new, prev, exact in cases:
+        gi = single.load_adjacency(a)
+        r = [single.find_inliers_raw(gi, pkg.CLIQUE_HEU), single.find_inliers_raw(gi, pkg.CLIQUE_HEU_INCREMENTAL, num_new, prev)]
+        if exact:
+            r.append(single.find_inliers_raw(gi, pkg.CLIQUE_EXACT))
+        want.append(r)
+    single.close()
+
+    def work(h):
+        res = []
+        for a, num_new, prev, exact in cases:
+            gi = h.load_adjacency(a)
+            r = [h.find_inliers_raw(gi, pkg.CLIQUE_HEU), h.find_inliers_raw(gi, pkg.CLIQUE_HEU_INCREMENTAL, num_new, prev)]
+            if exact:
+                r.append(h.find_inliers_raw(gi, pkg.CLIQUE_EXACT))
+            res.append(r)
+        return res
+
+    got, calls = run_sharded(world, lambda r: PcmGpu(3, 0, rank=r, world=world), work)
+    assert calls > 0
+    for r in range(world):
+        for c, (w, g_) in enumerate(zip(want, got[r])):
+            for m, (x, y) in enumerate(zip(w, g_)):
+                assert x[0] == y[0] and x[1].tolist() == y[1].tolist(), (r, c, m)
+                if m == 0:
+                    assert x[2].tolist() == y[2].tolist(), (r, c)
+
+
+def test_sharded_heuristic_on_pcm_graph():
+    """the same on a real PCM adjacency (2000 closures): sharded == single, and fewer chains per rank"""
+    from gpu_common import run_sharded
+    gph = synth.config2(seed=9, P=2500, n=2000)
+    one = PcmGpu(3, 0, odom_threshold=-1, lc_threshold=5.0)
+    one.update(gph["odom"], gph["values"])
+    one.update(gph["lcs"], [])
+    adj, _ = one.group_adj(0, with_dist=False)
+    k, ids, true = one.find_inliers_raw(0, pkg.CLIQUE_HEU)
+    one.close()
+
+    def work(h):
+        gi = h.load_adjacency(adj)
+        return h.find_inliers_raw(gi, pkg.CLIQUE_HEU)
+
+    got, calls = run_sharded(4, lambda r: PcmGpu(3, 0, rank=r, world=4), work)
+    for kk, ii, tt in got:
+        assert kk == k and ii.tolist() == ids.tolist() and tt.tolist() == true.tolist()
