@@ -13,6 +13,7 @@
  * implicit contraction; all fused operations are explicit fma() calls in rpgo_math.cuh).
  */
 #include <cstdio>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -185,14 +186,196 @@ __global__ void __launch_bounds__(32) traj_fold_warp_kernel(int n_chains, const 
   }
 }
 
+/* K1, batched exact fold (MODE_PCM, default).  Same arithmetic, same order as the kernel above (bit-identical), but
+ * everything that does not depend on the running value is taken off the sequential path:
+ *   - the factors of the next 32 steps are copied global -> shared asynchronously (cp.async) while the current 32
+ *     steps are folded, so the chain never waits on HBM;
+ *   - a parallel "prep" phase (one thread per step) builds Ad(delta^-1), the NaN-masked delta covariance and the
+ *     rotation_info flag of each step;
+ *   - warp 0 folds the covariance with one or two elements per lane (18 lanes in 3D, 9 in 2D: the sequential path
+ *     is ~25 FP64 operations and two shuffle hops per step), warp 1 folds the pose: two independent chains. */
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+template <int D>
+__global__ void __launch_bounds__(64) traj_fold_batched_kernel(int n_chains, const FoldChain* __restrict__ chains,
+                                                               const int32_t* __restrict__ out_idx,
+                                                               const double* __restrict__ dpose,
+                                                               const double* __restrict__ dcov, double* entries) {
+  constexpr int E = Dim<D>::ENTRY, PS = Dim<D>::PS, N = Dim<D>::N, NN = N * N, OC = Dim<D>::OFF_COV, RD = Dim<D>::RD,
+                TD = Dim<D>::TD, HS = (D == 3 ? 18 : 9), B = 32;
+  __shared__ __align__(16) double raw_pose[B * PS];
+  __shared__ __align__(16) double raw_cov[B * NN];
+  __shared__ __align__(16) double cH[2][B * HS];
+  __shared__ __align__(16) double cDc[2][B * NN];
+  __shared__ __align__(16) double cDl[2][B * PS];
+  __shared__ int cOut[2][B];
+  __shared__ int cRot[2][B];
+  const int c = blockIdx.x;
+  if (c >= n_chains) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const FoldChain ch = chains[c];
+  if (ch.n_steps <= 0) return;
+  const int nb = (ch.n_steps + B - 1) / B;
+  /* warp 0: lane (r, cg) owns the covariance elements (r, cg) and, in 3D, (r, cg + 3): 3N lanes are active */
+  constexpr int CPL = (D == 3 ? 2 : 1);
+  const int ll = lane < 3 * N ? lane : 0;
+  const int r = ll / 3, cg = ll % 3;
+
+  auto issue_raw = [&](int b) {
+    const size_t k0 = (size_t)ch.first_step + (size_t)b * B;
+    const int cnt = min(B, ch.n_steps - b * B);
+    for (int i = tid; i < cnt * PS; i += 64) cp_async8(&raw_pose[i], dpose + k0 * PS + i);
+    for (int i = tid; i < cnt * NN; i += 64) cp_async8(&raw_cov[i], dcov + k0 * NN + i);
+  };
+  auto prep = [&](int b) {
+    const int cnt = min(B, ch.n_steps - b * B);
+    const int st = b & 1;
+    if (tid < cnt) {
+      Pose<D> Dl;
+#pragma unroll
+      for (int i = 0; i < PS; ++i) Dl.m[i] = raw_pose[tid * PS + i];
+      /* from_factor: NaN rotation covariance => keep only the translation block (GeometryUtils.h:98-113) */
+      double tr = raw_cov[tid * NN];
+#pragma unroll
+      for (int i = 1; i < RD; ++i) tr = tr + raw_cov[tid * NN + i * N + i];
+      const bool drot = !(tr != tr);
+#pragma unroll
+      for (int rr = 0; rr < N; ++rr)
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          double v = raw_cov[tid * NN + rr * N + j];
+          if (!drot) v = (rr >= RD && j >= RD && rr < RD + TD && j < RD + TD) ? v : 0.0;
+          cDc[st][tid * NN + rr * N + j] = v;
+        }
+      const Adj<D> H = adjoint<D>(inverse<D>(Dl));
+#pragma unroll
+      for (int i = 0; i < HS; ++i) cH[st][tid * HS + i] = H.h[i];
+#pragma unroll
+      for (int i = 0; i < PS; ++i) cDl[st][tid * PS + i] = Dl.m[i];
+      cRot[st][tid] = drot ? 1 : 0;
+      cOut[st][tid] = out_idx[(size_t)ch.first_step + (size_t)b * B + tid];
+    }
+  };
+
+  /* running state */
+  Pose<D> P;
+  double S[CPL];
+  bool rot = true;
+  if (warp == 0) {
+#pragma unroll
+    for (int cc = 0; cc < CPL; ++cc) S[cc] = entries[(size_t)ch.start_idx * E + OC + r * N + cg + 3 * cc];
+  } else {
+    load_pose<D>(entries + (size_t)ch.start_idx * E, 1, P);
+    rot = entries[(size_t)ch.start_idx * E + Dim<D>::OFF_ROT] != 0.0;
+  }
+
+  issue_raw(0);
+  cp_async_wait_all();
+  __syncthreads();
+  prep(0);
+  __syncthreads();
+  for (int b = 0; b < nb; ++b) {
+    const int st = b & 1;
+    const int cnt = min(B, ch.n_steps - b * B);
+    if (b + 1 < nb) issue_raw(b + 1); /* in flight during the chain phase */
+    if (warp == 0) {
+      for (int i = 0; i < cnt; ++i) {
+        const double* Hh = cH[st] + i * HS;
+        const double* Dc = cDc[st] + i * NN + r * N + cg;
+        /* row r of H: columns 0..2 (hr) and, for 3D rows >= 3, columns 3..5 (ar) */
+        const double* hr = (D == 3) ? Hh + (r < 3 ? r * 3 : 9 + (r - 3) * 3) : Hh + r * 3;
+        const double h0 = hr[0], h1 = hr[1], h2 = hr[2];
+        /* t[cc] = (H S)(r, cg + 3 cc), k-order; S(k, j) lives in lane (k, cg) */
+        double t[CPL];
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) {
+          const double s0 = __shfl_sync(0xffffffffu, S[cc], 0 * 3 + cg);
+          const double s1 = __shfl_sync(0xffffffffu, S[cc], 1 * 3 + cg);
+          const double s2 = __shfl_sync(0xffffffffu, S[cc], 2 * 3 + cg);
+          t[cc] = dot3(h0, h1, h2, s0, s1, s2);
+        }
+        if (D == 3) {
+          const double* ar = Hh + (r < 3 ? r : r - 3) * 3;
+          const double a0 = ar[0], a1 = ar[1], a2 = ar[2];
+#pragma unroll
+          for (int cc = 0; cc < CPL; ++cc) {
+            const double s3 = __shfl_sync(0xffffffffu, S[cc], 3 * 3 + cg);
+            const double s4 = __shfl_sync(0xffffffffu, S[cc], 4 * 3 + cg);
+            const double s5 = __shfl_sync(0xffffffffu, S[cc], 5 * 3 + cg);
+            if (r >= 3) {
+              t[cc] = fma(a0, s3, t[cc]);
+              t[cc] = fma(a1, s4, t[cc]);
+              t[cc] = fma(a2, s5, t[cc]);
+            }
+          }
+        }
+        /* the full row r of t: element j = g + 3 cc sits in lane (r, g) */
+        double tf[N];
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc)
+#pragma unroll
+          for (int g = 0; g < 3; ++g) tf[g + 3 * cc] = __shfl_sync(0xffffffffu, t[cc], r * 3 + g);
+        /* out(r, j) = t(r, :) . H(j, :) + Dc(r, j) */
+        const double* Aj = Hh + cg * 3;
+        S[0] = dot3(tf[0], tf[1], tf[2], Aj[0], Aj[1], Aj[2]) + Dc[0];
+        if (D == 3) {
+          const double* Bj = Hh + 9 + cg * 3;
+          double acc = dot3(tf[0], tf[1], tf[2], Bj[0], Bj[1], Bj[2]);
+          acc = fma(tf[3 % N], Aj[0], acc);
+          acc = fma(tf[4 % N], Aj[1], acc);
+          acc = fma(tf[5 % N], Aj[2], acc);
+          S[CPL - 1] = acc + Dc[3 % N];
+        }
+        if (lane < 3 * N) {
+          double* o = entries + (size_t)cOut[st][i] * E + OC + r * N + cg;
+#pragma unroll
+          for (int cc = 0; cc < CPL; ++cc) o[3 * cc] = S[cc];
+        }
+      }
+    } else {
+      for (int i = 0; i < cnt; ++i) {
+        Pose<D> Dl;
+#pragma unroll
+        for (int q = 0; q < PS; ++q) Dl.m[q] = cDl[st][i * PS + q];
+        P = compose<D>(P, Dl);
+        rot = rot && (cRot[st][i] != 0);
+        if (lane == 0) {
+          double* o = entries + (size_t)cOut[st][i] * E;
+#pragma unroll
+          for (int q = 0; q < PS; ++q) o[q] = P.m[q];
+          o[Dim<D>::OFF_ROT] = rot ? 1.0 : 0.0;
+          o[Dim<D>::OFF_NODE] = 0.0;
+        }
+      }
+    }
+    if (b + 1 < nb) {
+      cp_async_wait_all();
+      __syncthreads();
+      prep(b + 1);
+    }
+    __syncthreads();
+  }
+}
+
 void launch_traj_fold(int dim, int mode, int n_chains, const FoldChain* chains, const int32_t* out_idx,
                       const double* delta_pose, const double* delta_cov, double* entries, cudaStream_t st) {
   if (n_chains <= 0) return;
   /* one chain per block so that independent robots land on different SMs */
   const int blocks = n_chains;
   if (mode == MODE_PCM) {
-    if (dim == 3) traj_fold_warp_kernel<3><<<blocks, 32, 0, st>>>(n_chains, chains, out_idx, delta_pose, delta_cov, entries);
-    else traj_fold_warp_kernel<2><<<blocks, 32, 0, st>>>(n_chains, chains, out_idx, delta_pose, delta_cov, entries);
+    static const bool v1 = getenv("RPGO_FOLD_V1") != nullptr; /* A/B knob: the one-warp kernel */
+    if (v1) {
+      if (dim == 3) traj_fold_warp_kernel<3><<<blocks, 32, 0, st>>>(n_chains, chains, out_idx, delta_pose, delta_cov, entries);
+      else traj_fold_warp_kernel<2><<<blocks, 32, 0, st>>>(n_chains, chains, out_idx, delta_pose, delta_cov, entries);
+    } else {
+      if (dim == 3) traj_fold_batched_kernel<3><<<blocks, 64, 0, st>>>(n_chains, chains, out_idx, delta_pose, delta_cov, entries);
+      else traj_fold_batched_kernel<2><<<blocks, 64, 0, st>>>(n_chains, chains, out_idx, delta_pose, delta_cov, entries);
+    }
     return;
   }
 #define CALL(D, M) traj_fold_kernel<D, M><<<blocks, 1, 0, st>>>(n_chains, chains, out_idx, delta_pose, delta_cov, entries)
