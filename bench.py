@@ -249,6 +249,14 @@ def main():
                            "pairwise_tiled_kernel<3>" if a.kernel in (2, 20, 21, 22, 23, 24) else "pairwise_grouped_kernel<3,12,3,512>"),
                 "peak_source": "measured live by rpgo_fp64_peak (DFMA micro-benchmark; MEASURED_PEAKS.json has no FP64 entry)",
                 "algorithmic_flop_per_pair": FLOP_PER_PAIR_3D_PCM, "kernel_ms": k3_ms}
+    # DRAM traffic of that kernel from the committed ncu --set full capture of this very configuration (one GPU)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_k3_traffic.json")))
+        if tr["kernel"] == roofline["kernel"] and a.closures == 50000 and world == 1:
+            roofline["traffic"] = tr["traffic_bytes_per_launch"]
+            roofline["traffic_source"] = tr["source"]
+    except (OSError, KeyError, ValueError):
+        pass
 
     # ---- e2e through the public host API, host buffers ---------------------------------------------
     e2e = None
