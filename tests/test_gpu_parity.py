@@ -535,3 +535,17 @@ def test_sharded_heuristic_on_pcm_graph():
     got, calls = run_sharded(4, lambda r: PcmGpu(3, 0, rank=r, world=4), work)
     for kk, ii, tt in got:
         assert kk == k and ii.tolist() == ids.tolist() and tt.tolist() == true.tolist()
+
+
+def test_clique_exact_warp_kernel_midsize():
+    """K5 warp kernel (n <= 1024: colouring bound + edge-task frontier) against the reference FMC on graphs where the
+    frontier really splits roots over many warps; the block kernel (n > 1024) is covered by the planted case above."""
+    rng = np.random.default_rng(26)
+    ref = orc.ref_clique_exact if orc.ref_fmc() is not None else orc.clique_exact
+    g = PcmGpu(3, 0)
+    for n, p in [(400, 0.3), (1000, 0.12), (64, 0.85), (33, 1.0), (32, 0.0), (1024, 0.05)]:
+        a = rand_graph(rng, n, p)
+        gi = g.load_adjacency(a)
+        k, ids, _ = g.find_inliers_raw(gi, pkg.CLIQUE_EXACT)
+        kr, ir = ref(a)
+        assert k == kr and ids.tolist() == ir.tolist(), (n, p, ids.tolist(), ir.tolist())
