@@ -33,6 +33,12 @@
 namespace rpgo {
 
 static constexpr int HEU_THREADS = 128;
+/* measurement build (-DRPGO_CLIQUE_COUNTERS): ctl[1] chains started, ctl[2] windows, ctl[3] adjacency/degree-mask bytes read */
+#ifdef RPGO_CLIQUE_COUNTERS
+#define RPGO_COUNT_BYTES(ctl, x) atomicAdd((ctl) + 3, (unsigned long long)(x))
+#else
+#define RPGO_COUNT_BYTES(ctl, x) ((void)0)
+#endif
 static constexpr int HEU_PRE = 13; /* words per thread covered by the sweep prefetch (13 * 128 * 32 = 53k vertices) */
 
 __global__ void degmask_kernel(const int32_t* __restrict__ deg, int n, int M, uint32_t* mask, int words) {
@@ -159,7 +165,10 @@ __device__ int heu_list_tail(const uint32_t* __restrict__ bits, int64_t stride32
       if (alive[k]) {
         const int pos = k * HEU_THREADS + tid;
         if (pos == first) alive[k] = false;
-        else alive[k] = (prow[u[k] >> 5] >> (u[k] & 31)) & 1u;
+        else {
+          alive[k] = (prow[u[k] >> 5] >> (u[k] & 31)) & 1u;
+          RPGO_COUNT_BYTES(ctl, 4);
+        }
       }
     }
     m -= 1; /* refined at the top of the next iteration */
@@ -211,6 +220,7 @@ __global__ void __launch_bounds__(HEU_THREADS) heu_round_kernel(const uint32_t* 
     int cnt = 0, top = -1;
     for (int w = tid; w < W; w += blockDim.x) {
       const uint32_t r = bits[(size_t)v * stride32 + w] & degmask[w];
+      RPGO_COUNT_BYTES(ctl, 8);
       R[w] = r;
       cnt += __popc(r);
       if (r) top = w;
@@ -247,6 +257,7 @@ __global__ void __launch_bounds__(HEU_THREADS) heu_round_kernel(const uint32_t* 
        * that both dependent global accesses overlap: one memory round trip per window */
       uint32_t rw = 0;
       if ((T >> lane) & 1u) rw = bits[(size_t)(t * 32 + lane) * stride32 + t];
+      if (tid < 32 && ((T >> lane) & 1u)) RPGO_COUNT_BYTES(ctl, 4);
       const int nT = __popc(T);
       uint32_t pre[4][HEU_PRE]; /* up to 4 candidate rows x HEU_PRE words per thread are prefetched */
       const bool prefetch = (nT <= 4) && (t <= HEU_PRE * HEU_THREADS);
@@ -260,6 +271,7 @@ __global__ void __launch_bounds__(HEU_THREADS) heu_round_kernel(const uint32_t* 
           for (int k = 0; k < HEU_PRE; ++k) {
             const int w = tid + k * HEU_THREADS;
             pre[c][k] = (b >= 0 && w < t) ? bits[(size_t)(t * 32 + b) * stride32 + w] : 0xffffffffu;
+            if (b >= 0 && w < t) RPGO_COUNT_BYTES(ctl, 4);
           }
         }
       }
@@ -311,6 +323,7 @@ __global__ void __launch_bounds__(HEU_THREADS) heu_round_kernel(const uint32_t* 
               const int b = 31 - __clz(q);
               q &= ~(1u << b);
               r &= bits[(size_t)(t * 32 + b) * stride32 + w];
+              RPGO_COUNT_BYTES(ctl, 4);
             }
             R[w] = r;
             cnt += __popc(r);
@@ -444,7 +457,7 @@ int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_
   while (start < n) {
     t_round0 = now_ms();
     const unsigned long long none = ~0ULL;
-    const unsigned long long init3[3] = {none, 0ULL, 0ULL};
+    const unsigned long long init3[4] = {none, 0ULL, 0ULL, 0ULL};
     CUCHECK(cudaMemcpyAsync(s.ctl, init3, sizeof(init3), cudaMemcpyHostToDevice, st));
     degmask_kernel<<<(W + 127) / 128, 128, 0, st>>>(deg, n, M, s.degmask, W);
     /* candidates of this rank: v = start (mod nothing) for one GPU, v = rank (mod world) when partitioned */
@@ -470,10 +483,10 @@ int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_
     }
     if (trace) {
       fprintf(stderr, "[clique] rank %d round kernel+sync %.3f ms\n", rank, now_ms() - t_round0);
-      unsigned long long c[3];
+      unsigned long long c[4];
       cudaMemcpy(c, s.ctl, sizeof(c), cudaMemcpyDeviceToHost);
-      fprintf(stderr, "[clique] round start=%d M=%d grid=%d -> improver=%lld icc=%d | chains started %llu, windows %llu\n", start, M, grid,
-              h_ctl == none ? -1LL : (long long)(h_ctl >> 32), (int)(h_ctl & 0xffffffffu), c[1], c[2]);
+      fprintf(stderr, "[clique] round start=%d M=%d grid=%d -> improver=%lld icc=%d | chains started %llu, windows %llu, bytes %llu\n", start, M, grid,
+              h_ctl == none ? -1LL : (long long)(h_ctl >> 32), (int)(h_ctl & 0xffffffffu), c[1], c[2], c[3]);
     }
     if (h_ctl == none) break;
     winner = (int)(h_ctl >> 32);
@@ -513,7 +526,7 @@ int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_
   if (!winner_local) {
     /* the final winning chain ran on another rank: replay that one candidate here (same bound, same filter) to get
      * its pick log; intermediate winners only moved the bound and need no log */
-    const unsigned long long init3[3] = {~0ULL, 0ULL, 0ULL};
+    const unsigned long long init3[4] = {~0ULL, 0ULL, 0ULL, 0ULL};
     CUCHECK(cudaMemcpyAsync(s.ctl, init3, sizeof(init3), cudaMemcpyHostToDevice, st));
     CUCHECK(cudaMemsetAsync(s.elim + winner, 0, sizeof(int32_t), st));
     degmask_kernel<<<(W + 127) / 128, 128, 0, st>>>(deg, n, winner_M, s.degmask, W);
