@@ -415,6 +415,15 @@ void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, co
   const int cb_begin = j_begin / 32;
   const int cb_end = (g.n + 31) / 32;
   dim3 grid((g.n + TILE_SEG - 1) / TILE_SEG, cb_end - cb_begin);
+  /* few work items (small groups, or a handful of new columns in the online case): short row segments, so that the
+   * launch fills the SMs and a block is 4 iterations long instead of 43 (latency of a single-closure update) */
+  const long long items512 = (long long)((g.n + TILE_SEG - 1) / TILE_SEG) * (cb_end - cb_begin);
+  const bool small = items512 < 4LL * 148;
+  if (g_tiled_variant == 6 && small) {
+    if (dim == 3) launch_grouped<3, 12, 3, 48>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st);
+    else launch_grouped<2, 12, 3, 48>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st);
+    return;
+  }
   if (dim == 3 && g_tiled_variant >= 5) {
     switch (g_tiled_variant) {
       case 5: launch_grouped<3, 12, 2, 512>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); break;
