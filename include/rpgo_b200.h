@@ -144,6 +144,16 @@ int rpgo_lc_remove_last(rpgo_handle* h, int32_t g, uint64_t* key_from, uint64_t*
 int rpgo_find_inliers(rpgo_handle* h, int32_t g, int32_t clique_mode, int64_t n_new, int64_t prev_size,
                       int32_t* ids_out, int64_t* size_out, int32_t* true_clique_out);
 
+/* Batched form for the groups of one removeOutliers() call (Pcm::findInliers loops over all ObservationId groups,
+ * Pcm.h:858-876; the groups are independent).  Entry k searches group groups[k] with n_new[k] / prev_size[k]
+ * (both arrays may be NULL for the non-incremental modes) and writes its ids to ids_out + ids_offset[k] (capacity >=
+ * that group's size) and its size to size_out[k] — same values rpgo_find_inliers returns.  The searches run
+ * concurrently on internal streams.  With cfg.world > 1 and an exchange function registered, whole groups are assigned
+ * to ranks (entry k to rank k mod world) and the results are combined with one all-reduce. */
+int rpgo_find_inliers_batch(rpgo_handle* h, int32_t n_groups, const int32_t* groups, int32_t clique_mode,
+                            const int64_t* n_new, const int64_t* prev_size, int32_t* ids_out, const int64_t* ids_offset,
+                            int64_t* size_out);
+
 /* ---- multi-GPU inlier selection: candidate partition + incumbent exchange ------------------------------
  * With cfg.world > 1 and an exchange function registered, rpgo_find_inliers partitions the clique search's root
  * candidates over the ranks (candidate v belongs to rank v mod world in the heuristic, root n-1-v likewise in the

@@ -43,6 +43,7 @@ SYMBOLS = [
     ("rpgo_find_group", C.c_int32, [C.c_void_p, C.c_uint8, C.c_uint8]),
     ("rpgo_lc_remove_last", C.c_int, [C.c_void_p, C.c_int32, c_u64p, c_u64p]),
     ("rpgo_find_inliers", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, c_i32p, c_i64p, c_i32p]),
+    ("rpgo_find_inliers_batch", C.c_int, [C.c_void_p, C.c_int32, c_i32p, C.c_int32, c_i64p, c_i64p, c_i32p, c_i64p, c_i64p]),
     ("rpgo_set_exchange", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("rpgo_frame_align_measurements", C.c_int, [C.c_void_p, C.c_int32, C.c_uint8, C.c_int64, c_i32p, c_dp]),
     ("rpgo_robot_odom_values", C.c_int, [C.c_void_p, C.c_uint8, c_dp, C.c_int64, c_u64p, c_dp, c_i64p]),

@@ -14,10 +14,14 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <ctime>
 #include <cstring>
 #include <map>
 #include <set>
+#include <atomic>
+#include <climits>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -130,6 +134,19 @@ PinBuf& pinned_staging() {
 
 }  // namespace
 
+static constexpr int64_t CLIQUE_BLOCKS = 148 * 8;
+struct CliqueSet {
+  DevBuf degmask, picks, elim, result, ctl, rwork;
+  void wire(Arena* a) {
+    for (DevBuf* b : {&degmask, &picks, &elim, &result, &ctl, &rwork}) b->arena = a;
+  }
+};
+struct CliqueWorker {
+  CliqueSet set;
+  cudaStream_t stream = nullptr;
+  explicit CliqueWorker(Arena* a) { set.wire(a); }
+};
+
 struct rpgo_handle {
   Arena arena;
   rpgo_cfg cfg;
@@ -157,15 +174,23 @@ struct rpgo_handle {
   /* staging (the pinned host buffer is per thread, shared by successive handles: cudaMallocHost is slow) */
   DevBuf d_stage;
   DevBuf d_lcent, d_ok, d_dist, d_scan;
-  /* clique scratch */
-  DevBuf c_degmask, c_picks, c_elim, c_result, c_ctl, c_rwork;
+  /* clique scratch: one set for the single-group entry point, one per worker of the batched one */
+  CliqueSet cset;
+  std::vector<CliqueWorker*> workers;
 
   void wire() {
     arena.st = stream;
-    for (DevBuf* b : {&traj, &d_stage, &d_lcent, &d_ok, &d_dist, &d_scan, &c_degmask, &c_picks, &c_elim, &c_result, &c_ctl, &c_rwork})
+    for (DevBuf* b : {&traj, &d_stage, &d_lcent, &d_ok, &d_dist, &d_scan, &cset.degmask, &cset.picks, &cset.elim, &cset.result, &cset.ctl, &cset.rwork})
       b->arena = &arena;
   }
   ~rpgo_handle() {
+    for (CliqueWorker* w : workers) {
+      if (w->stream) {
+        cudaStreamSynchronize(w->stream);
+        cudaStreamDestroy(w->stream);
+      }
+      delete w;
+    }
     for (Group* g : groups) delete g;
     if (stream) {
       arena.release();
@@ -613,6 +638,19 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
   if (!key_from || !key_to || !pose || !cov) return RPGO_ERR_INVALID;
   const int E = h->E, PS = h->PS, NN = h->NN;
   cudaStream_t st = h->stream;
+  static const bool trace = getenv("RPGO_TRACE") != nullptr;
+  auto now_ms = []() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  };
+  double t_mark = trace ? now_ms() : 0.0;
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    const double t = now_ms();
+    fprintf(stderr, "[lc_append n=%lld] %-28s %8.3f ms\n", (long long)n, what, t - t_mark);
+    t_mark = t;
+  };
 
   if (h->traj_dirty) {
     /* the reference looks trajectory entries up at every pair check (GraphUtils.h:40-42), so closures
@@ -656,6 +694,7 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
     if (p_if[k] == 0 && !h->key2idx.count(key_from[k])) h->missing_refs.insert(key_from[k]);
     if (p_ib[k] == 0 && !h->key2idx.count(key_to[k])) h->missing_refs.insert(key_to[k]);
   }
+  mark("stage + key lookups (host)");
   H_CHECK_CUDA(h, h->d_stage.ensure(total, 0, st));
   H_CHECK_CUDA(h, h->d_lcent.ensure((size_t)n * E * 8, 0, st));
   H_CHECK_CUDA(h, h->d_ok.ensure((size_t)n, 0, st));
@@ -679,6 +718,7 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
   }
   H_CHECK_CUDA(h, cudaStreamSynchronize(st));
   (void)h_dist;
+  mark("H2D + K2 + D2H (sync)");
 
   /* host pass 2: grouping in arrival order (Pcm.h:466-486) */
   std::map<int32_t, int64_t> old_n; /* groups touched -> size before this call */
@@ -725,6 +765,7 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
     /* remember group in the low bits via a side vector */
     need.resize(h->groups.size(), 0);
   }
+  mark("grouping (host)");
   /* capacities (n was advanced above; ensure_group must see the old n for its copies) */
   for (auto& kv : old_n) {
     Group* g = h->groups[kv.first];
@@ -734,6 +775,7 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
     g->n = n_new;
     if (rc != RPGO_OK) return rc;
   }
+  mark("ensure_group (alloc/copies)");
   /* destination addresses */
   {
     std::map<int32_t, int64_t> cursor = old_n;
@@ -755,6 +797,7 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
     H_CHECK_CUDA(h, cudaMemcpyAsync(g->idxb.as<int32_t>() + o, g->h_idxb.data() + o, (size_t)m * 4, cudaMemcpyHostToDevice, st));
     H_CHECK_CUDA(h, cudaMemcpyAsync(g->pfx.as<uint8_t>() + o, g->h_pfx.data() + o, (size_t)m, cudaMemcpyHostToDevice, st));
   }
+  mark("scatter + index uploads");
   /* K3 per touched group */
   for (auto& kv : old_n) {
     Group* g = h->groups[kv.first];
@@ -766,7 +809,9 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
     }
   }
   H_CHECK_CUDA(h, cudaGetLastError());
+  mark("K3 + finalize launches");
   H_CHECK_CUDA(h, cudaStreamSynchronize(st)); /* host vectors / pinned staging are reused */
+  mark("final sync");
   return RPGO_OK;
 }
 
@@ -910,6 +955,52 @@ int rpgo_lc_remove_last(rpgo_handle* h, int32_t gi, uint64_t* key_from, uint64_t
 }
 
 /* ---------------------------------------------------------------------------------------------- */
+/* one clique search on an explicit scratch set / stream (shared by the single and the batched entry point) */
+static int run_clique(rpgo_handle* h, Group* g, int32_t clique_mode, int64_t n_new, int64_t prev_size, CliqueSet* cset,
+                      cudaStream_t st, CliqueShard cs, int32_t* ids_out, int64_t* size_out, int32_t* true_clique_out,
+                      int64_t* launches, std::string* err) {
+  const int n = (int)g->n;
+  CliqueScratch s;
+  s.degmask = cset->degmask.as<uint32_t>();
+  s.picks = cset->picks.as<int32_t>();
+  s.elim = cset->elim.as<int32_t>();
+  s.result = cset->result.as<int32_t>();
+  s.ctl = cset->ctl.as<long long>();
+  s.rwork = cset->rwork.as<uint32_t>();
+  s.rwork_blocks = CLIQUE_BLOCKS;
+  int r;
+  if (clique_mode == RPGO_CLIQUE_HEU) {
+    r = clique_heuristic(g->bits.as<uint32_t>(), g->stride32, n, g->deg.as<int32_t>(), 0, -1, s, ids_out, true_clique_out,
+                         launches, st, cs);
+    if (r < -1) { *err = "clique_heuristic failed: " + std::to_string(r); return RPGO_ERR_CUDA; }
+    *size_out = r;
+  } else if (clique_mode == RPGO_CLIQUE_HEU_INCREMENTAL) {
+    if (n_new < 0 || n_new > n || prev_size < 0) return RPGO_ERR_INVALID;
+    r = clique_heuristic(g->bits.as<uint32_t>(), g->stride32, n, g->deg.as<int32_t>(), (int)(n - n_new), (int)prev_size, s,
+                         ids_out, true_clique_out, launches, st, cs);
+    if (r < -1) { *err = "clique_heuristic failed: " + std::to_string(r); return RPGO_ERR_CUDA; }
+    *size_out = (r > prev_size) ? r : 0; /* GraphUtils.cpp:40-43 */
+  } else if (clique_mode == RPGO_CLIQUE_EXACT) {
+    r = clique_exact(g->bits.as<uint32_t>(), g->stride32, n, g->deg.as<int32_t>(), s, ids_out, launches, st, cs);
+    if (r < 0) { *err = "clique_exact failed: " + std::to_string(r); return RPGO_ERR_CUDA; }
+    *size_out = r;
+  } else {
+    return RPGO_ERR_INVALID;
+  }
+  return RPGO_OK;
+}
+
+static cudaError_t ensure_clique_set(CliqueSet* c, int n, cudaStream_t st) {
+  const int W = (n + 31) / 32;
+  cudaError_t e;
+  if ((e = c->degmask.ensure((size_t)W * 4 + 64, 0, st)) != cudaSuccess) return e;
+  if ((e = c->picks.ensure((size_t)n * 4 + 64, 0, st)) != cudaSuccess) return e;
+  if ((e = c->elim.ensure((size_t)n * 4 + 64, 0, st)) != cudaSuccess) return e;
+  if ((e = c->result.ensure((size_t)n * 4 + 64, 0, st)) != cudaSuccess) return e;
+  if ((e = c->ctl.ensure(64, 0, st)) != cudaSuccess) return e;
+  return c->rwork.ensure((size_t)CLIQUE_BLOCKS * n * 4 + (size_t)W * 8 + 64, 0, st);
+}
+
 int rpgo_find_inliers(rpgo_handle* h, int32_t gi, int32_t clique_mode, int64_t n_new, int64_t prev_size,
                       int32_t* ids_out, int64_t* size_out, int32_t* true_clique_out) {
   if (!h || !ids_out || !size_out) return RPGO_ERR_INVALID;
@@ -918,45 +1009,104 @@ int rpgo_find_inliers(rpgo_handle* h, int32_t gi, int32_t clique_mode, int64_t n
   const int n = (int)g->n;
   if (n <= 0 || (!h->loop_check && !g->landmark)) { h->err = "find_inliers: empty group or loop check disabled"; return RPGO_ERR_INVALID; }
   cudaStream_t st = h->stream;
-  const int W = (n + 31) / 32;
-  const int64_t blocks = 148 * 8;
-  H_CHECK_CUDA(h, h->c_degmask.ensure((size_t)W * 4 + 64, 0, st));
-  H_CHECK_CUDA(h, h->c_picks.ensure((size_t)n * 4 + 64, 0, st));
-  H_CHECK_CUDA(h, h->c_elim.ensure((size_t)n * 4 + 64, 0, st));
-  H_CHECK_CUDA(h, h->c_result.ensure((size_t)n * 4 + 64, 0, st));
-  H_CHECK_CUDA(h, h->c_ctl.ensure(64, 0, st));
-  H_CHECK_CUDA(h, h->c_rwork.ensure((size_t)blocks * n * 4 + (size_t)W * 8 + 64, 0, st));
-  CliqueScratch s;
-  s.degmask = h->c_degmask.as<uint32_t>();
-  s.picks = h->c_picks.as<int32_t>();
-  s.elim = h->c_elim.as<int32_t>();
-  s.result = h->c_result.as<int32_t>();
-  s.ctl = h->c_ctl.as<long long>();
-  s.rwork = h->c_rwork.as<uint32_t>();
-  s.rwork_blocks = blocks;
-  int r;
+  H_CHECK_CUDA(h, ensure_clique_set(&h->cset, n, st));
   CliqueShard cs;
   cs.rank = h->cfg.rank;
   cs.world = h->cfg.world;
   cs.exchange = h->xchg;
   cs.user = h->xchg_user;
-  if (clique_mode == RPGO_CLIQUE_HEU) {
-    r = clique_heuristic(g->bits.as<uint32_t>(), g->stride32, n, g->deg.as<int32_t>(), 0, -1, s, ids_out, true_clique_out,
-                         &h->launches, st, cs);
-    if (r < -1) { h->err = "clique_heuristic failed: " + std::to_string(r); return RPGO_ERR_CUDA; }
-    *size_out = r;
-  } else if (clique_mode == RPGO_CLIQUE_HEU_INCREMENTAL) {
-    if (n_new < 0 || n_new > n || prev_size < 0) return RPGO_ERR_INVALID;
-    r = clique_heuristic(g->bits.as<uint32_t>(), g->stride32, n, g->deg.as<int32_t>(), (int)(n - n_new), (int)prev_size, s,
-                         ids_out, true_clique_out, &h->launches, st, cs);
-    if (r < -1) { h->err = "clique_heuristic failed: " + std::to_string(r); return RPGO_ERR_CUDA; }
-    *size_out = (r > prev_size) ? r : 0; /* GraphUtils.cpp:40-43 */
-  } else if (clique_mode == RPGO_CLIQUE_EXACT) {
-    r = clique_exact(g->bits.as<uint32_t>(), g->stride32, n, g->deg.as<int32_t>(), s, ids_out, &h->launches, st, cs);
-    if (r < 0) { h->err = "clique_exact failed: " + std::to_string(r); return RPGO_ERR_CUDA; }
-    *size_out = r;
+  return run_clique(h, g, clique_mode, n_new, prev_size, &h->cset, st, cs, ids_out, size_out, true_clique_out, &h->launches,
+                    &h->err);
+}
+
+/* Batched inlier selection: the groups of one removeOutliers() call are independent (Pcm::findInliers loops over
+ * them, Pcm.h:858-876), so their searches run concurrently — a few host threads, each with its own stream and
+ * scratch set, pull groups (largest first) from a shared counter.  With cfg.world > 1 and an exchange registered,
+ * whole groups are assigned to ranks (entry k -> rank k mod world) and the results are combined with ONE all-reduce. */
+int rpgo_find_inliers_batch(rpgo_handle* h, int32_t n_groups, const int32_t* groups, int32_t clique_mode,
+                            const int64_t* n_new, const int64_t* prev_size, int32_t* ids_out, const int64_t* ids_offset,
+                            int64_t* size_out) {
+  if (!h || n_groups < 0 || (n_groups > 0 && (!groups || !ids_out || !ids_offset || !size_out))) return RPGO_ERR_INVALID;
+  if (n_groups == 0) return RPGO_OK;
+  int max_n = 0;
+  for (int k = 0; k < n_groups; ++k) {
+    if (groups[k] < 0 || groups[k] >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
+    Group* g = h->groups[groups[k]];
+    if (g->n <= 0 || (!h->loop_check && !g->landmark)) { h->err = "find_inliers_batch: empty group or loop check disabled"; return RPGO_ERR_INVALID; }
+    max_n = std::max<int>(max_n, (int)g->n);
+  }
+  const bool spread = h->cfg.world > 1 && h->xchg != nullptr;
+  const int world = spread ? h->cfg.world : 1, rank = spread ? h->cfg.rank : 0;
+  /* workers: bounded by the scratch they need (the pick logs are CLIQUE_BLOCKS x n ints each) */
+  const size_t per_set = (size_t)CLIQUE_BLOCKS * max_n * 4 + (size_t)max_n * 16;
+  int T = (int)std::min<size_t>(8, std::max<size_t>(1, ((size_t)2 << 30) / std::max<size_t>(per_set, 1)));
+  T = std::min(T, (n_groups + world - 1) / world);
+  while ((int)h->workers.size() < T) {
+    CliqueWorker* w = new CliqueWorker(&h->arena);
+    if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) { delete w; h->err = "stream creation failed"; return RPGO_ERR_CUDA; }
+    h->workers.push_back(w);
+  }
+  /* everything the searches read was produced on the handle's stream */
+  cudaEvent_t ready;
+  H_CHECK_CUDA(h, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  for (int t = 0; t < T; ++t) H_CHECK_CUDA(h, ensure_clique_set(&h->workers[t]->set, max_n, h->stream)); /* arena: this thread only */
+  H_CHECK_CUDA(h, cudaEventRecord(ready, h->stream));
+  for (int t = 0; t < T; ++t) H_CHECK_CUDA(h, cudaStreamWaitEvent(h->workers[t]->stream, ready, 0));
+  /* this rank's entries, largest group first */
+  std::vector<int> order;
+  for (int k = 0; k < n_groups; ++k)
+    if (k % world == rank) order.push_back(k);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h->groups[groups[a]]->n > h->groups[groups[b]]->n; });
+  std::atomic<int> next(0);
+  std::vector<int> rcs(T, RPGO_OK);
+  std::vector<std::string> errs(T);
+  std::vector<int64_t> launches(T, 0);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto body = [&](int t) {
+    cudaSetDevice(dev);
+    CliqueWorker* w = h->workers[t];
+    for (;;) {
+      const int q = next.fetch_add(1);
+      if (q >= (int)order.size()) break;
+      const int k = order[q];
+      Group* g = h->groups[groups[k]];
+      const int rc = run_clique(h, g, clique_mode, n_new ? n_new[k] : 0, prev_size ? prev_size[k] : 0, &w->set, w->stream,
+                                CliqueShard(), ids_out + ids_offset[k], size_out + k, nullptr, &launches[t], &errs[t]);
+      if (rc != RPGO_OK) { rcs[t] = rc; break; }
+    }
+    cudaStreamSynchronize(w->stream);
+  };
+  if (T == 1) {
+    body(0);
   } else {
-    return RPGO_ERR_INVALID;
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t) th.emplace_back(body, t);
+    for (auto& x : th) x.join();
+  }
+  cudaEventDestroy(ready);
+  for (int t = 0; t < T; ++t) {
+    h->launches += launches[t];
+    if (rcs[t] != RPGO_OK) { h->err = errs[t]; return rcs[t]; }
+  }
+  if (spread) {
+    /* one MAX all-reduce over [size_k, ids_k...] for all entries: non-owners contribute the minimum */
+    std::vector<long long> buf;
+    for (int k = 0; k < n_groups; ++k) {
+      const bool mine = (k % world == rank);
+      const int64_t cap = h->groups[groups[k]]->n;
+      buf.push_back(mine ? (long long)size_out[k] : LLONG_MIN);
+      for (int64_t i = 0; i < cap; ++i)
+        buf.push_back(mine && i < std::max<int64_t>(size_out[k], 0) ? (long long)ids_out[ids_offset[k] + i] : LLONG_MIN);
+    }
+    if (h->xchg(h->xchg_user, RPGO_XCHG_MAX_I64, buf.data(), (int64_t)buf.size(), 0) != 0) { h->err = "exchange failed"; return RPGO_ERR_CUDA; }
+    size_t pos = 0;
+    for (int k = 0; k < n_groups; ++k) {
+      const int64_t cap = h->groups[groups[k]]->n;
+      size_out[k] = (int64_t)buf[pos++];
+      for (int64_t i = 0; i < cap; ++i, ++pos)
+        if (i < std::max<int64_t>(size_out[k], 0)) ids_out[ids_offset[k] + i] = (int32_t)buf[pos];
+    }
   }
   return RPGO_OK;
 }

@@ -418,13 +418,34 @@ class PcmGpu : public OutlierRemovalT<P> {
   }
   void findInliers() {                                                               // Pcm.h:851-876
     total_good_lc_ = 0;
+    // the groups are independent: one batched call searches them concurrently (rpgo_find_inliers_batch)
+    std::vector<int32_t> todo;
+    std::vector<int64_t> offset;
+    int64_t total = 0;
     for (size_t g = 0; g < groups_.size(); ++g) {
       Group& m = groups_[g];
       if (m.factors.size() == 0) { m.consistent_factors = Graph(); continue; }
-      if (loop_check_ || m.is_landmark) selectInliers((int)g, RPGO_CLIQUE_HEU, 0, 0, false);   // landmarks: Pcm.h:878-895
-      else m.consistent_factors = m.factors;
-      total_good_lc_ += m.consistent_factors.size();
+      if (loop_check_ || m.is_landmark) {                                             // landmarks: Pcm.h:878-895
+        todo.push_back((int32_t)g);
+        offset.push_back(total);
+        total += (int64_t)m.factors.size();
+      } else {
+        m.consistent_factors = m.factors;
+      }
     }
+    if (!todo.empty()) {
+      std::vector<int32_t> ids((size_t)std::max<int64_t>(total, 1));
+      std::vector<int64_t> sizes(todo.size(), 0);
+      check(rpgo_find_inliers_batch(h_, (int32_t)todo.size(), todo.data(), RPGO_CLIQUE_HEU, nullptr, nullptr, ids.data(),
+                                    offset.data(), sizes.data()), "rpgo_find_inliers_batch");
+      for (size_t q = 0; q < todo.size(); ++q) {
+        Group& m = groups_[todo[q]];
+        m.consistent_factors = Graph();
+        m.inlier_idx.assign(ids.begin() + offset[q], ids.begin() + offset[q] + sizes[q]);
+        for (int64_t i = 0; i < sizes[q]; ++i) m.consistent_factors.add(m.factors[ids[offset[q] + i]]);   // Pcm.h:867-869
+      }
+    }
+    for (auto& m : groups_) total_good_lc_ += m.consistent_factors.size();
   }
   void findInliersIncremental(const std::map<int, size_t>& num_new) {                // Pcm.h:906-947
     for (auto& kv : num_new)

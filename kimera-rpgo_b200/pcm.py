@@ -350,26 +350,51 @@ class PcmGpu:
         k = int(size.value)
         return k, ids[:max(k, 0)].copy(), true[:max(k, 0)].copy()
 
+    def find_inliers_batch(self, groups, clique_mode=CLIQUE_HEU, n_new=None, prev_size=None):
+        """rpgo_find_inliers_batch: [(size, ids)] for the given group ordinals, searched concurrently."""
+        groups = [int(g) for g in groups]
+        if not groups:
+            return []
+        caps = np.array([max(len(self.group_factors[g]), 1) for g in groups], dtype=np.int64)
+        off = np.zeros(len(groups), dtype=np.int64)
+        off[1:] = np.cumsum(caps)[:-1]
+        ids = np.zeros(int(caps.sum()), dtype=np.int32)
+        sizes = np.zeros(len(groups), dtype=np.int64)
+        garr = np.array(groups, dtype=np.int32)
+        nn = None if n_new is None else np.ascontiguousarray(n_new, dtype=np.int64)
+        pv = None if prev_size is None else np.ascontiguousarray(prev_size, dtype=np.int64)
+        self._check(self.lib.rpgo_find_inliers_batch(
+            self.h, len(groups), garr.ctypes.data_as(_capi.c_i32p), clique_mode,
+            None if nn is None else nn.ctypes.data_as(_capi.c_i64p), None if pv is None else pv.ctypes.data_as(_capi.c_i64p),
+            ids.ctypes.data_as(_capi.c_i32p), off.ctypes.data_as(_capi.c_i64p), sizes.ctypes.data_as(_capi.c_i64p)),
+            "rpgo_find_inliers_batch")
+        return [(int(sizes[k]), ids[off[k]:off[k] + max(int(sizes[k]), 0)].copy()) for k in range(len(groups))]
+
     def _find_inliers(self):  # Pcm.h:851-899
         self.total_good_lc = 0
+        todo = []
         for g in self.group_order:
             fs = self.group_factors[g]
             if self.loop_check:
                 if len(fs) == 0:
                     self.group_consistent[g] = []
                     continue
-                k, ids, _ = self.find_inliers_raw(g, CLIQUE_HEU)
-                self.group_consistent[g] = [fs[i] for i in ids[:k]]
+                todo.append(g)
             else:
                 self.group_consistent[g] = list(fs)
-            self.total_good_lc += len(self.group_consistent[g])
+        # the groups are independent: one batched call (rpgo_find_inliers_batch) searches them concurrently
+        for g, (k, ids) in zip(todo, self.find_inliers_batch(todo, CLIQUE_HEU)):
+            fs = self.group_factors[g]
+            self.group_consistent[g] = [fs[i] for i in ids[:k]]
+        self.total_good_lc = sum(len(self.group_consistent[g]) for g in self.group_order)
         self._landmark_inliers()
 
     def _find_inliers_incremental(self, num_new):  # Pcm.h:906-970
-        for g, nn in num_new.items():
+        gs = list(num_new.keys())
+        prevs = [len(self.group_consistent[g]) for g in gs]
+        res = self.find_inliers_batch(gs, CLIQUE_HEU_INCREMENTAL, [num_new[g] for g in gs], prevs)
+        for g, (k, ids) in zip(gs, res):
             fs = self.group_factors[g]
-            prev = len(self.group_consistent[g])
-            k, ids, _ = self.find_inliers_raw(g, CLIQUE_HEU_INCREMENTAL, nn, prev)
             if k > 0:
                 self.group_consistent[g] = [fs[i] for i in ids[:k]]
         self.total_good_lc = sum(len(self.group_consistent[g]) for g in self.group_order)

@@ -549,3 +549,62 @@ def test_clique_exact_warp_kernel_midsize():
         k, ids, _ = g.find_inliers_raw(gi, pkg.CLIQUE_EXACT)
         kr, ir = ref(a)
         assert k == kr and ids.tolist() == ir.tolist(), (n, p, ids.tolist(), ir.tolist())
+
+
+def _multi_group_handle(**kw):
+    gph = synth.config4(seed=11, robots=4, P=600, n=3000, outlier_frac=0.3)
+    g = PcmGpu(3, 0, odom_threshold=30.0, lc_threshold=5.0, **kw)
+    arr = synth.as_arrays(gph)
+    g.odom_append_arrays(arr["o_prev"], arr["o_new"], arr["o_pose"], arr["o_cov"], arr["o_init"])
+    return g, arr
+
+
+def test_find_inliers_batch_equals_per_group():
+    """rpgo_find_inliers_batch (concurrent searches on worker streams) == rpgo_find_inliers group by group, for the
+    heuristic, the incremental heuristic and the exact mode."""
+    g, arr = _multi_group_handle()
+    g.lc_append_arrays(arr["l_from"], arr["l_to"], arr["l_pose"], arr["l_cov"])
+    groups = sorted(g.group_factors)
+    assert len(groups) == 10
+    single = [g.find_inliers_raw(gi, pkg.CLIQUE_HEU) for gi in groups]
+    batch = g.find_inliers_batch(groups, pkg.CLIQUE_HEU)
+    for (k, ids, _), (kb, ib) in zip(single, batch):
+        assert k == kb and ids.tolist() == ib.tolist()
+    nn = [max(1, len(g.group_factors[gi]) // 3) for gi in groups]
+    pv = [3 + (gi % 4) for gi in groups]
+    single = [g.find_inliers_raw(gi, pkg.CLIQUE_HEU_INCREMENTAL, a, b) for gi, a, b in zip(groups, nn, pv)]
+    batch = g.find_inliers_batch(groups, pkg.CLIQUE_HEU_INCREMENTAL, nn, pv)
+    for (k, ids, _), (kb, ib) in zip(single, batch):
+        assert k == kb and ids.tolist() == ib.tolist()
+    # exact mode on sparser copies of the adjacencies (keeps the search short)
+    rng = np.random.default_rng(3)
+    small = []
+    for q in range(6):
+        a = rand_graph(rng, int(rng.integers(20, 80)), rng.uniform(0.2, 0.7))
+        small.append(g.load_adjacency(a, c1=chr(ord('m') + q), c2='z'))
+    single = [g.find_inliers_raw(gi, pkg.CLIQUE_EXACT) for gi in small]
+    batch = g.find_inliers_batch(small, pkg.CLIQUE_EXACT)
+    for (k, ids, _), (kb, ib) in zip(single, batch):
+        assert k == kb and ids.tolist() == ib.tolist()
+    g.close()
+
+
+def test_find_inliers_batch_spread_over_ranks():
+    """with an exchange registered the batch assigns whole groups to ranks and combines with one all-reduce"""
+    from gpu_common import run_sharded
+    ref, arr = _multi_group_handle()
+    ref.lc_append_arrays(arr["l_from"], arr["l_to"], arr["l_pose"], arr["l_cov"])
+    groups = sorted(ref.group_factors)
+    want = ref.find_inliers_batch(groups, pkg.CLIQUE_HEU)
+    adjs = [ref.group_adj(gi, with_dist=False)[0] for gi in groups]
+    ref.close()
+
+    def work(h):
+        gl = [h.load_adjacency(a, c1=chr(ord('a') + q), c2='z') for q, a in enumerate(adjs)]
+        return h.find_inliers_batch(gl, pkg.CLIQUE_HEU)
+
+    got, calls = run_sharded(3, lambda r: PcmGpu(3, 0, rank=r, world=3), work)
+    assert calls == 1
+    for res in got:
+        for (k, ids), (kb, ib) in zip(want, res):
+            assert k == kb and ids.tolist() == ib.tolist()

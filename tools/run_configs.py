@@ -37,7 +37,12 @@ def timed_update(g, arr):
         sizes[gi] = k
     g.sync()
     t3 = time.perf_counter()
-    return dict(odom_ms=(t1 - t0) * 1e3, lc_append_ms=(t2 - t1) * 1e3, clique_ms=(t3 - t2) * 1e3, accepted=int(acc.sum()),
+    batch = g.find_inliers_batch(sorted(num_new), pkg.CLIQUE_HEU)   # the same searches, concurrently
+    g.sync()
+    t4 = time.perf_counter()
+    assert [b[0] for b in batch] == [sizes[gi] for gi in sorted(num_new)]
+    return dict(odom_ms=(t1 - t0) * 1e3, lc_append_ms=(t2 - t1) * 1e3, clique_ms=(t3 - t2) * 1e3,
+                clique_batch_ms=(t4 - t3) * 1e3, accepted=int(acc.sum()),
                 inliers=int(sum(sizes.values())), groups=len(sizes))
 
 
