@@ -154,6 +154,7 @@ struct rpgo_handle {
   bool odom_check = true, loop_check = true;
   Thresholds th;
   cudaStream_t stream = nullptr;
+  cudaEvent_t ev_stage = nullptr; /* marks the end of the last H2D copy out of the pinned staging buffer */
   std::string err;
   int64_t launches = 0;
   rpgo_exchange_fn xchg = nullptr; /* incumbent exchange of the sharded clique searches */
@@ -197,6 +198,7 @@ struct rpgo_handle {
       cudaStreamSynchronize(stream);
       cudaStreamDestroy(stream);
     }
+    if (ev_stage) cudaEventDestroy(ev_stage);
   }
 };
 
@@ -403,6 +405,10 @@ int rpgo_create(const rpgo_cfg* cfg, rpgo_handle** out) {
     return RPGO_ERR_CUDA;
   }
   h->wire();
+  if (cudaEventCreateWithFlags(&h->ev_stage, cudaEventDisableTiming) != cudaSuccess) {
+    delete h;
+    return RPGO_ERR_CUDA;
+  }
   {
     /* keep freed arena chunks cached in the device's default pool across handles */
     int dev = 0;
@@ -556,6 +562,7 @@ int rpgo_odom_append(rpgo_handle* h, int64_t n, const uint64_t* prev_key, const 
   }
   H_CHECK_CUDA(h, h->d_stage.ensure(total, 0, st));
   H_CHECK_CUDA(h, cudaMemcpyAsync(h->d_stage.p, pin, total, cudaMemcpyHostToDevice, st));
+  H_CHECK_CUDA(h, cudaEventRecord(h->ev_stage, st));
   char* d = (char*)h->d_stage.p;
   const double* d_pose = (const double*)d;
   const double* d_cov = (const double*)(d + off_cov);
@@ -607,7 +614,9 @@ int rpgo_odom_append(rpgo_handle* h, int64_t n, const uint64_t* prev_key, const 
   }
   H_CHECK_CUDA(h, cudaGetLastError());
   h->traj_n = new_entries;
-  H_CHECK_CUDA(h, cudaStreamSynchronize(st)); /* pinned staging is reused by the next call */
+  /* the pinned staging buffer is reused by the next call: wait for the H2D copy only, the fold itself keeps running
+   * while the caller prepares the loop closures (everything downstream is ordered on the same stream) */
+  H_CHECK_CUDA(h, cudaEventSynchronize(h->ev_stage));
   return RPGO_OK;
 }
 
