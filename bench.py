@@ -246,7 +246,7 @@ def main():
     achieved = FLOP_PER_PAIR_3D_PCM * (pairs / world) / (k3_ms * 1e-3) / 1e12
     roofline = {"bound": "fp64", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s", "frac": achieved / tf.value,
                 "traffic": None, "kernel": ("pairwise_direct_kernel<3>" if a.kernel in (1, 13, 14) else
-                           "pairwise_tiled_kernel<3>" if a.kernel in (2, 20, 21, 22, 23, 24) else "pairwise_grouped_kernel<3,12,3,512>"),
+                           "pairwise_tiled_kernel<3>" if a.kernel in (2, 20, 21, 22, 23, 24) else "pairwise_grouped_kernel<3,12,3,504>"),
                 "peak_source": "measured live by rpgo_fp64_peak (DFMA micro-benchmark; MEASURED_PEAKS.json has no FP64 entry)",
                 "algorithmic_flop_per_pair": FLOP_PER_PAIR_3D_PCM, "kernel_ms": k3_ms}
     # DRAM traffic of that kernel from the committed ncu --set full capture of this very configuration (one GPU)

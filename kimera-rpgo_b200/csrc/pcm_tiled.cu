@@ -427,8 +427,8 @@ void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, co
   if (dim == 3 && g_tiled_variant >= 5) {
     switch (g_tiled_variant) {
       case 5: launch_grouped<3, 12, 2, 512>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); break;
-      case 6: launch_grouped<3, 12, 3, 512>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); break;
-      case 7: launch_grouped<3, 12, 3, 1024>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); break;
+      case 6: launch_grouped<3, 12, 3, 504>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); break; /* 42 x 12 rows: no ragged last iteration */
+      case 7: launch_grouped<3, 12, 3, 512>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); break;
       case 10: launch_grouped<3, 12, 6, 512>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); break;
       case 11: launch_grouped<3, 12, 12, 512>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); break;
       case 8: launch_grouped<3, 12, 4, 512>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); break;
