@@ -28,6 +28,8 @@
 #include <ctime>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "kernels.cuh"
 
 namespace rpgo {
@@ -194,11 +196,9 @@ __global__ void undead_kernel(const uint32_t* __restrict__ bits, int64_t stride3
 
 /* ctl[0]: packed (candidate << 32 | icc) of the lowest-index improving candidate of this round
  *         (ULLONG_MAX = none).  picks_block: per-block pick log (n ints each). */
-__global__ void __launch_bounds__(HEU_THREADS) heu_round_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n,
-                                                                const int32_t* __restrict__ deg,
-                                                                const uint32_t* __restrict__ degmask, int first, int vstep,
-                                                                int M, unsigned long long* ctl, int32_t* picks_block,
-                                                                int32_t* dead_flags) {
+__device__ __forceinline__ void heu_round_body(const uint32_t* __restrict__ bits, int64_t stride32, int n,
+                                               const int32_t* __restrict__ deg, const uint32_t* degmask, int first, int vstep,
+                                               int M, unsigned long long* ctl, int32_t* picks_block, int32_t* dead_flags) {
   extern __shared__ uint32_t R[];
   __shared__ int sh[64];
   __shared__ int s_abort;
@@ -346,6 +346,87 @@ __global__ void __launch_bounds__(HEU_THREADS) heu_round_kernel(const uint32_t* 
   }
 }
 
+__global__ void __launch_bounds__(HEU_THREADS) heu_round_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n,
+                                                                const int32_t* __restrict__ deg,
+                                                                const uint32_t* __restrict__ degmask, int first, int vstep,
+                                                                int M, unsigned long long* ctl, int32_t* picks_block,
+                                                                int32_t* dead_flags) {
+  heu_round_body(bits, stride32, n, deg, degmask, first, vstep, M, ctl, picks_block, dead_flags);
+}
+
+/* All rounds of one search in ONE cooperative launch (single-rank searches): the bound update, the winner's pick log and
+ * the invalidation of cached verdicts move onto the device, separated by grid-wide barriers, so a search costs one launch
+ * and one host synchronisation instead of ~7 API calls per round.  Same rounds, same order of events as the host loop. */
+struct HeuResult {
+  int M, winner, winner_M, winner_icc, rounds, pad;
+};
+
+__global__ void __launch_bounds__(HEU_THREADS) heu_persistent_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n,
+                                                                     const int32_t* __restrict__ deg, uint32_t* degmask,
+                                                                     int first, int maxclq0, unsigned long long* ctl,
+                                                                     int32_t* picks_block, int32_t* dead_flags,
+                                                                     int32_t* picks_out, HeuResult* result) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const int W = (n + 31) / 32;
+  const int tid = threadIdx.x;
+  const long long gtid = (long long)blockIdx.x * blockDim.x + tid, gthreads = (long long)gridDim.x * blockDim.x;
+  int M = maxclq0, start = first < 0 ? 0 : first;
+  int winner = -1, winner_M = 0, winner_icc = 0, rounds = 0;
+  while (start < n) {
+    /* degree filter of this bound, control word */
+    for (long long w = gtid; w < W; w += gthreads) {
+      uint32_t m = 0;
+#pragma unroll 4
+      for (int b = 0; b < 32; ++b) {
+        const int u = (int)w * 32 + b;
+        if (u < n && deg[u] >= M) m |= 1u << b;
+      }
+      degmask[w] = m;
+    }
+    if (gtid == 0) ctl[0] = ~0ULL;
+    grid.sync();
+    heu_round_body(bits, stride32, n, deg, degmask, start, 1, M, ctl, picks_block, dead_flags);
+    grid.sync();
+    ++rounds;
+    const unsigned long long c = *(volatile unsigned long long*)ctl;
+    if (c == ~0ULL) break;
+    const int v = (int)(c >> 32), icc = (int)(c & 0xffffffffu);
+    /* the winner's block keeps its pick log */
+    if ((int)blockIdx.x == (v - start) % (int)gridDim.x) {
+      const int32_t* my_picks = picks_block + (size_t)blockIdx.x * n;
+      for (int k = tid; k < icc - 1; k += blockDim.x) picks_out[k] = my_picks[k];
+    }
+    /* a vertex with M <= deg < icc leaves the degree filter: cached verdicts of its neighbours are no longer valid */
+    for (int u = blockIdx.x; u < n; u += gridDim.x) {
+      const int d = deg[u];
+      if (d >= M && d < icc) {
+        for (int w = tid; w < W; w += blockDim.x) {
+          uint32_t r = bits[(size_t)u * stride32 + w];
+          while (r) {
+            const int b = __ffs(r) - 1;
+            r &= r - 1;
+            dead_flags[w * 32 + b] = 0;
+          }
+        }
+        if (tid == 0) dead_flags[u] = 0;
+      }
+    }
+    winner = v;
+    winner_M = M;
+    winner_icc = icc;
+    M = icc;
+    start = v + 1;
+    grid.sync();
+  }
+  if (gtid == 0) {
+    result->M = M;
+    result->winner = winner;
+    result->winner_M = winner_M;
+    result->winner_icc = winner_icc;
+    result->rounds = rounds;
+  }
+}
+
 /* elimination step of every vertex of the winner's initial list:
  * e(u) = k such that u leaves the list when pick p_k is applied (p_1 > p_2 > ... > p_K), 0 if u was
  * never in the list.  u leaves at the first (= highest-id) pick it is not adjacent to.
@@ -441,15 +522,61 @@ int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_
   };
   const double t_begin = now_ms();
   double t_round0 = 0;
-  std::vector<int32_t> hdeg(n);
-  CUCHECK(cudaMemcpyAsync(hdeg.data(), deg, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  static const bool host_loop = getenv("RPGO_CLIQUE_HOSTLOOP") != nullptr;
+  const bool persistent = !sharded && !trace && !host_loop;
+  std::vector<int32_t> hdeg;
   CUCHECK(cudaMemsetAsync(s.elim, 0, sizeof(int32_t) * n, st));
-  CUCHECK(cudaStreamSynchronize(st));
+  if (!persistent) { /* the host loop needs the degrees for the cache invalidation */
+    hdeg.resize(n);
+    CUCHECK(cudaMemcpyAsync(hdeg.data(), deg, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    CUCHECK(cudaStreamSynchronize(st));
+  }
   std::vector<int32_t> changed; /* vertices whose filter membership changes between two bounds */
   int M = maxclq0;
   int winner = -1, winner_M = 0, winner_icc = 0, winner_block = 0;
   bool winner_local = true;
   int start = first < 0 ? 0 : first;
+  if (persistent) {
+    /* single rank: all rounds in one cooperative launch */
+    static bool attr2 = false;
+    if (!attr2) {
+      cudaFuncSetAttribute(heu_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr2 = true;
+    }
+    int dev = 0, sms = 0, bps = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    CUCHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, heu_persistent_kernel, HEU_THREADS, smem));
+    if (bps >= 1) {
+      int grid = bps * sms;
+      if (grid > (int)s.rwork_blocks) grid = (int)s.rwork_blocks;
+      /* small groups take a slice of the machine so that independent searches (batched entry point) run side by side */
+      const int want = std::max(64, (n - start + 7) / 8);
+      if (grid > want) grid = want;
+      if (grid > n - start) grid = std::max(1, n - start);
+      HeuResult* d_res = (HeuResult*)((unsigned long long*)s.ctl + 4);
+      const uint32_t* a_bits = bits;
+      int64_t a_stride = stride32;
+      int a_n = n, a_first = start, a_M = maxclq0;
+      const int32_t* a_deg = deg;
+      uint32_t* a_degmask = s.degmask;
+      unsigned long long* a_ctl = (unsigned long long*)s.ctl;
+      int32_t* a_rwork = (int32_t*)s.rwork;
+      int32_t* a_elim = s.elim;
+      int32_t* a_picks = s.picks;
+      void* args[] = {&a_bits, &a_stride, &a_n, &a_deg, &a_degmask, &a_first, &a_M, &a_ctl, &a_rwork, &a_elim, &a_picks, &d_res};
+      CUCHECK(cudaLaunchCooperativeKernel((void*)heu_persistent_kernel, dim3(grid), dim3(HEU_THREADS), args, smem, st));
+      *launches += 1;
+      HeuResult hr;
+      CUCHECK(cudaMemcpyAsync(&hr, d_res, sizeof(hr), cudaMemcpyDeviceToHost, st));
+      CUCHECK(cudaStreamSynchronize(st));
+      M = hr.M;
+      winner = hr.winner;
+      winner_M = hr.winner_M;
+      winner_icc = hr.winner_icc;
+      start = n; /* the host loop below is skipped */
+    }
+  }
   std::vector<int32_t> picks_host;
   const int grid_cap = (int)s.rwork_blocks;
   unsigned long long h_ctl;
