@@ -716,9 +716,6 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
   h->launches++;
   H_CHECK_CUDA(h, cudaGetLastError());
   uint8_t* h_ok = (uint8_t*)(pin + total);
-  double* h_dist = (double*)(pin + ((total + (size_t)n + 15) & ~size_t(15)));
-  /* h_dist region: make sure it is inside the pinned buffer */
-  h_dist = nullptr;
   std::vector<double> dist_host;
   H_CHECK_CUDA(h, cudaMemcpyAsync(h_ok, h->d_ok.p, (size_t)n, cudaMemcpyDeviceToHost, st));
   if (odom_dist) {
@@ -726,7 +723,6 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
     H_CHECK_CUDA(h, cudaMemcpyAsync(dist_host.data(), h->d_dist.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
   }
   H_CHECK_CUDA(h, cudaStreamSynchronize(st));
-  (void)h_dist;
   mark("H2D + K2 + D2H (sync)");
 
   /* host pass 2: grouping in arrival order (Pcm.h:466-486) */

@@ -57,8 +57,6 @@ __global__ void __launch_bounds__(EX_THREADS) exact_kernel(const uint32_t* __res
   const int tid = threadIdx.x;
   uint32_t* stack = stacks + (size_t)blockIdx.x * (size_t)(depth_max + 1) * W;
   int32_t* path = paths + (size_t)blockIdx.x * (depth_max + 2);     /* path[0] = root, path[l] = pick at level l */
-  int32_t* cnts = path + 0;                                         /* (cnt kept in registers per level via recompute) */
-  (void)cnts;
   int32_t* best = best_paths + (size_t)blockIdx.x * (depth_max + 2);
 
   /* roots n-1-rank, n-1-rank-world, ...: this rank's share (world = 1: all of them) */

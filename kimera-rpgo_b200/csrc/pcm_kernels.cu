@@ -158,7 +158,6 @@ __global__ void __launch_bounds__(32) traj_fold_warp_kernel(int n_chains, const 
       for (int kk = 0; kk < 3; ++kk)
 #pragma unroll
         for (int j = 0; j < N; ++j) Sk[kk][j] = __shfl_sync(0xffffffffu, S[j], kk);
-#pragma unroll
       double g0 = H.h[0], g1 = H.h[1], g2 = H.h[2];
 #pragma unroll
       for (int i = 1; i < 3; ++i) {

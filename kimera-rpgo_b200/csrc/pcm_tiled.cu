@@ -7,12 +7,16 @@
  *     twice: array-of-structs (rows: the OLDER closure i, warp-uniform, read as broadcasts) and
  *     struct-of-arrays in slabs of 32 closures (columns: the NEWER closure j, one per lane, read
  *     conflict-free);
- *   - a thread block owns one slab of 32 columns and a segment of rows.  The column slab (38 KB) is
- *     brought in by ONE bulk TMA copy (cp.async.bulk ... mbarrier::complete_tx) and stays resident;
- *     the row records stream through a 2-stage TMA/mbarrier pipeline, 4 rows (one per warp) at a time;
- *   - one thread evaluates one pair with pair_check_v1 (single running covariance in registers,
- *     b_odom_d parked in a per-thread shared-memory scratch column); the 32 decisions of a warp are
- *     packed by __ballot_sync into the adjacency word (i, j/32).
+ *   - a thread block (12 warps, one block per SM) owns one slab of 32 columns and a segment of rows.  The column
+ *     slab (38 KB) is brought in by ONE bulk TMA copy (cp.async.bulk ... mbarrier::complete_tx) and stays
+ *     resident; the row records stream through 2-stage TMA/mbarrier pipelines, one row per warp;
+ *   - one thread evaluates one pair with the straight-line pair function (rpgo_pair_v2.cuh: single running
+ *     covariance in registers, b_odom_d parked in a per-thread shared-memory scratch column, rare reference
+ *     branches deferred to pair_check_exact); the 32 decisions of a warp are packed by __ballot_sync into
+ *     the adjacency word (i, j/32);
+ *   - pairwise_grouped_kernel (default) splits the block into three phase-shifted groups of four warps so that
+ *     FP64-saturated and latency-bound stages of different groups overlap; pairwise_tiled_kernel is the
+ *     one-group form kept for A/B measurements.
  * FP64 CUDA-core bound by design (6x6 / 3x3 fp64 with data-dependent branches: no tensor cores).
  */
 #include <cstdio>
@@ -106,7 +110,7 @@ template <int D, int TILE_WARPS, int MINB, int PAIRFN>
 __global__ void __launch_bounds__(TILE_WARPS * 32, MINB)
     pairwise_tiled_kernel(GroupView g, const double* __restrict__ aos, const double* __restrict__ soa, int j_begin,
                           int cb_begin, Shard sh, Thresholds th, Flagged fl) {
-  constexpr int RN = Rec<D>::N, E = Rec<D>::E;
+  constexpr int RN = Rec<D>::N;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* Jt = reinterpret_cast<double*>(smem_raw);
   double* It = reinterpret_cast<double*>(smem_raw + TiledSmem<D, TILE_WARPS>::JT);
