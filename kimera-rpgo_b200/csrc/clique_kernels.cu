@@ -34,7 +34,9 @@
 
 namespace rpgo {
 
-static constexpr int HEU_THREADS = 128;
+static constexpr int HEU_THREADS = 128;       /* block size of the clique kernels for n <= HEU_WIDE_N */
+static constexpr int HEU_THREADS_WIDE = 512;  /* wide rows (n > HEU_WIDE_N): 4x the sweep parallelism per chain */
+static constexpr int HEU_WIDE_N = 131072; /* measured: 512-thread blocks lose at 50k (27 vs 15 ms), win at 200k (911 vs 1038 ms) */
 /* measurement build (-DRPGO_CLIQUE_COUNTERS): ctl[1] chains started, ctl[2] windows, ctl[3] adjacency/degree-mask bytes read */
 #ifdef RPGO_CLIQUE_COUNTERS
 #define RPGO_COUNT_BYTES(ctl, x) atomicAdd((ctl) + 3, (unsigned long long)(x))
@@ -77,18 +79,19 @@ __device__ __forceinline__ void block_sum_max(int& s, int& m, int* sh) {
 
 
 static constexpr int HEU_LIST_K = 4;                       /* list elements per thread */
-static constexpr int HEU_LIST_MAX = HEU_LIST_K * HEU_THREADS;
+static constexpr int HEU_LIST_MAX = HEU_LIST_K * HEU_THREADS; /* list mode below this many survivors (any block size) */
 
 /* Tail of a greedy chain once at most HEU_LIST_MAX candidates survive: the survivors are written to shared
  * memory as a list in DESCENDING id order, so that "highest set bit of R" becomes "first live list entry"; each
  * pick then costs one adjacency word per live entry instead of a sweep over the whole bitset.  Same picks, same
  * order, same count as the bitset loop.  Returns the number of picks made (-1: a lower candidate already
  * improved, give up; -2: cannot beat M). */
+template <int TH>
 __device__ int heu_list_tail(const uint32_t* __restrict__ bits, int64_t stride32, const uint32_t* R, int top, int cnt,
                              int steps, int M, int v, unsigned long long* ctl, int32_t* my_picks, int32_t* L, int* sh) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   /* build the list: thread t owns the word range [top - (t+1)*C + 1, top - t*C] scanned from the top */
-  const int C = (top + HEU_THREADS) / HEU_THREADS;
+  const int C = (top + TH) / TH;
   int mine = 0;
   for (int c = 0; c < C; ++c) {
     const int w = top - tid * C - c;
@@ -118,11 +121,12 @@ __device__ int heu_list_tail(const uint32_t* __restrict__ bits, int64_t stride32
     }
   }
   __syncthreads();
-  int u[HEU_LIST_K];
-  bool alive[HEU_LIST_K];
+  constexpr int LK = (HEU_LIST_MAX + TH - 1) / TH; /* list elements per thread */
+  int u[LK];
+  bool alive[LK];
 #pragma unroll
-  for (int k = 0; k < HEU_LIST_K; ++k) {
-    const int pos = k * HEU_THREADS + tid;
+  for (int k = 0; k < LK; ++k) {
+    const int pos = k * TH + tid;
     alive[k] = pos < cnt;
     u[k] = alive[k] ? L[pos] : 0;
   }
@@ -132,9 +136,9 @@ __device__ int heu_list_tail(const uint32_t* __restrict__ bits, int64_t stride32
     /* first live entry (block-wide minimum position) and live count */
     int first = INT_MAX, live = 0;
 #pragma unroll
-    for (int k = 0; k < HEU_LIST_K; ++k) {
+    for (int k = 0; k < LK; ++k) {
       if (alive[k]) {
-        first = min(first, k * HEU_THREADS + tid);
+        first = min(first, k * TH + tid);
         ++live;
       }
     }
@@ -150,7 +154,7 @@ __device__ int heu_list_tail(const uint32_t* __restrict__ bits, int64_t stride32
     first = INT_MAX;
     live = 0;
 #pragma unroll
-    for (int i = 0; i < HEU_THREADS / 32; ++i) {
+    for (int i = 0; i < TH / 32; ++i) {
       first = min(first, sh[i]);
       live += sh[32 + i];
     }
@@ -163,9 +167,9 @@ __device__ int heu_list_tail(const uint32_t* __restrict__ bits, int64_t stride32
     ++made;
     const uint32_t* prow = bits + (size_t)pick * stride32;
 #pragma unroll
-    for (int k = 0; k < HEU_LIST_K; ++k) {
+    for (int k = 0; k < LK; ++k) {
       if (alive[k]) {
-        const int pos = k * HEU_THREADS + tid;
+        const int pos = k * TH + tid;
         if (pos == first) alive[k] = false;
         else {
           alive[k] = (prow[u[k] >> 5] >> (u[k] & 31)) & 1u;
@@ -196,6 +200,7 @@ __global__ void undead_kernel(const uint32_t* __restrict__ bits, int64_t stride3
 
 /* ctl[0]: packed (candidate << 32 | icc) of the lowest-index improving candidate of this round
  *         (ULLONG_MAX = none).  picks_block: per-block pick log (n ints each). */
+template <int TH>
 __device__ __forceinline__ void heu_round_body(const uint32_t* __restrict__ bits, int64_t stride32, int n,
                                                const int32_t* __restrict__ deg, const uint32_t* degmask, int first, int vstep,
                                                int M, unsigned long long* ctl, int32_t* picks_block, int32_t* dead_flags) {
@@ -239,7 +244,7 @@ __device__ __forceinline__ void heu_round_body(const uint32_t* __restrict__ bits
     while (cnt > 0) {
       if (steps + cnt + 1 <= M) { dead = true; break; }
       if (cnt <= HEU_LIST_MAX) {
-        const int made = heu_list_tail(bits, stride32, R, top, cnt, steps, M, v, ctl, my_picks, s_list, sh);
+        const int made = heu_list_tail<TH>(bits, stride32, R, top, cnt, steps, M, v, ctl, my_picks, s_list, sh);
         if (made == -1) return;
         if (made == -2) { dead = true; break; }
         steps += made;
@@ -260,7 +265,7 @@ __device__ __forceinline__ void heu_round_body(const uint32_t* __restrict__ bits
       if (tid < 32 && ((T >> lane) & 1u)) RPGO_COUNT_BYTES(ctl, 4);
       const int nT = __popc(T);
       uint32_t pre[4][HEU_PRE]; /* up to 4 candidate rows x HEU_PRE words per thread are prefetched */
-      const bool prefetch = (nT <= 4) && (t <= HEU_PRE * HEU_THREADS);
+      const bool prefetch = (nT <= 4) && (t <= HEU_PRE * TH);
       if (prefetch) {
         uint32_t q = T;
 #pragma unroll
@@ -269,7 +274,7 @@ __device__ __forceinline__ void heu_round_body(const uint32_t* __restrict__ bits
           if (b >= 0) q &= ~(1u << b);
 #pragma unroll
           for (int k = 0; k < HEU_PRE; ++k) {
-            const int w = tid + k * HEU_THREADS;
+            const int w = tid + k * TH;
             pre[c][k] = (b >= 0 && w < t) ? bits[(size_t)(t * 32 + b) * stride32 + w] : 0xffffffffu;
             if (b >= 0 && w < t) RPGO_COUNT_BYTES(ctl, 4);
           }
@@ -295,7 +300,7 @@ __device__ __forceinline__ void heu_round_body(const uint32_t* __restrict__ bits
         /* AND mask of the candidate rows that turned out to be picks */
 #pragma unroll
         for (int k = 0; k < HEU_PRE; ++k) {
-          const int w = tid + k * HEU_THREADS;
+          const int w = tid + k * TH;
           if (w < t) {
             uint32_t r = R[w];
             if (r) {
@@ -346,12 +351,13 @@ __device__ __forceinline__ void heu_round_body(const uint32_t* __restrict__ bits
   }
 }
 
-__global__ void __launch_bounds__(HEU_THREADS) heu_round_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n,
+template <int TH>
+__global__ void __launch_bounds__(TH) heu_round_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n,
                                                                 const int32_t* __restrict__ deg,
                                                                 const uint32_t* __restrict__ degmask, int first, int vstep,
                                                                 int M, unsigned long long* ctl, int32_t* picks_block,
                                                                 int32_t* dead_flags) {
-  heu_round_body(bits, stride32, n, deg, degmask, first, vstep, M, ctl, picks_block, dead_flags);
+  heu_round_body<TH>(bits, stride32, n, deg, degmask, first, vstep, M, ctl, picks_block, dead_flags);
 }
 
 /* All rounds of one search in ONE cooperative launch (single-rank searches): the bound update, the winner's pick log and
@@ -361,7 +367,8 @@ struct HeuResult {
   int M, winner, winner_M, winner_icc, rounds, pad;
 };
 
-__global__ void __launch_bounds__(HEU_THREADS) heu_persistent_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n,
+template <int TH>
+__global__ void __launch_bounds__(TH) heu_persistent_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n,
                                                                      const int32_t* __restrict__ deg, uint32_t* degmask,
                                                                      int first, int maxclq0, unsigned long long* ctl,
                                                                      int32_t* picks_block, int32_t* dead_flags,
@@ -385,7 +392,7 @@ __global__ void __launch_bounds__(HEU_THREADS) heu_persistent_kernel(const uint3
     }
     if (gtid == 0) ctl[0] = ~0ULL;
     grid.sync();
-    heu_round_body(bits, stride32, n, deg, degmask, start, 1, M, ctl, picks_block, dead_flags);
+    heu_round_body<TH>(bits, stride32, n, deg, degmask, start, 1, M, ctl, picks_block, dead_flags);
     grid.sync();
     ++rounds;
     const unsigned long long c = *(volatile unsigned long long*)ctl;
@@ -508,9 +515,13 @@ int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_
   if (smem > 200 * 1024) return -2; /* n > ~1.6M closures in one group: not supported by this kernel */
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(heu_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(heu_round_kernel<HEU_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(heu_round_kernel<HEU_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
+  static const char* wide_env = getenv("RPGO_CLIQUE_WIDE"); /* A/B knob: 0 / 1 forces the block size */
+  const bool wide = wide_env ? (wide_env[0] == '1') : (n > HEU_WIDE_N);
+  const int threads = wide ? HEU_THREADS_WIDE : HEU_THREADS;
   /* "dead" cache: a candidate that could not beat bound M cannot beat any M' >= M as long as its filtered
    * neighbourhood {u : deg(u) >= M} is unchanged, i.e. as long as no vertex has M <= deg < M'.  The host checks
    * that on the sorted degree list at every bound change and clears the cache otherwise. */
@@ -540,13 +551,16 @@ int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_
     /* single rank: all rounds in one cooperative launch */
     static bool attr2 = false;
     if (!attr2) {
-      cudaFuncSetAttribute(heu_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(heu_persistent_kernel<HEU_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(heu_persistent_kernel<HEU_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       attr2 = true;
     }
+    const void* pk = wide ? (const void*)heu_persistent_kernel<HEU_THREADS_WIDE> : (const void*)heu_persistent_kernel<HEU_THREADS>;
     int dev = 0, sms = 0, bps = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    CUCHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, heu_persistent_kernel, HEU_THREADS, smem));
+    if (wide) CUCHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, heu_persistent_kernel<HEU_THREADS_WIDE>, HEU_THREADS_WIDE, smem));
+    else CUCHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, heu_persistent_kernel<HEU_THREADS>, HEU_THREADS, smem));
     if (bps >= 1) {
       int grid = bps * sms;
       if (grid > (int)s.rwork_blocks) grid = (int)s.rwork_blocks;
@@ -565,7 +579,7 @@ int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_
       int32_t* a_elim = s.elim;
       int32_t* a_picks = s.picks;
       void* args[] = {&a_bits, &a_stride, &a_n, &a_deg, &a_degmask, &a_first, &a_M, &a_ctl, &a_rwork, &a_elim, &a_picks, &d_res};
-      CUCHECK(cudaLaunchCooperativeKernel((void*)heu_persistent_kernel, dim3(grid), dim3(HEU_THREADS), args, smem, st));
+      CUCHECK(cudaLaunchCooperativeKernel(pk, dim3(grid), dim3(threads), args, smem, st));
       *launches += 1;
       HeuResult hr;
       CUCHECK(cudaMemcpyAsync(&hr, d_res, sizeof(hr), cudaMemcpyDeviceToHost, st));
@@ -592,8 +606,12 @@ int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_
     int grid = (n - v0 + world - 1) / world;
     if (grid > grid_cap) grid = grid_cap;
     if (grid > 0) {
-      heu_round_kernel<<<grid, HEU_THREADS, smem, st>>>(bits, stride32, n, deg, s.degmask, v0, world, M,
-                                                        (unsigned long long*)s.ctl, (int32_t*)s.rwork, s.elim);
+      if (wide)
+        heu_round_kernel<HEU_THREADS_WIDE><<<grid, HEU_THREADS_WIDE, smem, st>>>(bits, stride32, n, deg, s.degmask, v0, world, M,
+                                                                             (unsigned long long*)s.ctl, (int32_t*)s.rwork, s.elim);
+      else
+        heu_round_kernel<HEU_THREADS><<<grid, HEU_THREADS, smem, st>>>(bits, stride32, n, deg, s.degmask, v0, world, M,
+                                                                     (unsigned long long*)s.ctl, (int32_t*)s.rwork, s.elim);
       *launches += 1;
     }
     *launches += 1;
@@ -657,8 +675,12 @@ int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_
     CUCHECK(cudaMemcpyAsync(s.ctl, init3, sizeof(init3), cudaMemcpyHostToDevice, st));
     CUCHECK(cudaMemsetAsync(s.elim + winner, 0, sizeof(int32_t), st));
     degmask_kernel<<<(W + 127) / 128, 128, 0, st>>>(deg, n, winner_M, s.degmask, W);
-    heu_round_kernel<<<1, HEU_THREADS, smem, st>>>(bits, stride32, n, deg, s.degmask, winner, n, winner_M,
-                                                   (unsigned long long*)s.ctl, (int32_t*)s.rwork, s.elim);
+    if (wide)
+      heu_round_kernel<HEU_THREADS_WIDE><<<1, HEU_THREADS_WIDE, smem, st>>>(bits, stride32, n, deg, s.degmask, winner, n, winner_M,
+                                                                        (unsigned long long*)s.ctl, (int32_t*)s.rwork, s.elim);
+    else
+      heu_round_kernel<HEU_THREADS><<<1, HEU_THREADS, smem, st>>>(bits, stride32, n, deg, s.degmask, winner, n, winner_M,
+                                                                (unsigned long long*)s.ctl, (int32_t*)s.rwork, s.elim);
     *launches += 2;
     CUCHECK(cudaMemcpyAsync(s.picks, (int32_t*)s.rwork, sizeof(int32_t) * (size_t)(K > 0 ? K : 0), cudaMemcpyDeviceToDevice, st));
   }
