@@ -317,6 +317,74 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 1)
   }
 }
 
+/* ---- column mode: a handful of NEW closures against all older ones (the online case) -----------------------
+ * With one new column the tiled kernels keep one lane per warp busy.  Here the roles of the operand layouts are swapped:
+ * the lanes of a warp are 32 consecutive OLDER closures i, read straight from their struct-of-arrays slab in global memory
+ * (every field load is one coalesced 256-byte line, L2-resident), and the NEW closure j is the warp-uniform operand (its
+ * array-of-structs record, staged in shared memory once per block).  Same pair function, same argument roles (i older,
+ * j newer), so the decisions are identical; bit (i, j) is set with atomicOr because a row word may receive several new
+ * columns from different blocks. */
+template <int D, int TILE_WARPS>
+__global__ void __launch_bounds__(TILE_WARPS * 32, 1)
+    pairwise_column_kernel(GroupView g, const double* __restrict__ aos, const double* __restrict__ soa, int j_begin, Shard sh,
+                           Thresholds th, Flagged fl) {
+  constexpr int RN = Rec<D>::N, E = Rec<D>::E;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* Jrec = reinterpret_cast<double*>(smem_raw);                 /* the new closure's record (RN doubles) */
+  double* Scr = reinterpret_cast<double*>(smem_raw + ((RN * 8 + 127) / 128) * 128);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int j = j_begin + blockIdx.y;
+  if (j >= g.n) return;
+  for (int f = tid; f < RN; f += blockDim.x) Jrec[f] = aos[(size_t)j * RN + f];
+  __syncthreads();
+  const int rs = blockIdx.x * TILE_WARPS + w; /* row slab of this warp */
+  const int i = rs * 32 + lane;
+  if (rs * 32 >= j) return;                   /* whole slab at or beyond the column: nothing below the diagonal here */
+  bool ok = false;
+  if (i < j && i < g.n && row_owned_t(sh, i)) {
+    const double* Il = soa + (size_t)rs * RN * 32 + lane; /* field f of closure i: Il[f * 32] */
+    const uint8_t pa = (uint8_t)Il[Rec<D>::OFF_PFX * 32];
+    const uint8_t pc = (uint8_t)Jrec[Rec<D>::OFF_PFX];
+    /* Pcm.h:691-698: if the prefixes of a and c differ, c and d swap (measurement not inverted) */
+    const double* Tc = (pa != pc) ? Jrec + Rec<D>::OFF_TB : Jrec + Rec<D>::OFF_TF;
+    const double* Td = (pa != pc) ? Jrec + Rec<D>::OFF_TF : Jrec + Rec<D>::OFF_TB;
+    double* scr = Scr + tid;
+    double dist;
+    bool near, bad;
+    ok = pair_check_v2<D>(Il + Rec<D>::OFF_TF * 32, 32, Il + Rec<D>::OFF_TB * 32, 32, Il + Rec<D>::OFF_LC * 32, 32, Tc, 1, Td, 1,
+                          Jrec + Rec<D>::OFF_LC, 1, scr, TILE_WARPS * 32, th, &dist, &near, &bad);
+    if (bad)
+      ok = pair_check_exact<D>(Il + Rec<D>::OFF_TF * 32, 32, Il + Rec<D>::OFF_TB * 32, 32, Il + Rec<D>::OFF_LC * 32, 32, Tc, 1, Td, 1,
+                               Jrec + Rec<D>::OFF_LC, 1, scr, TILE_WARPS * 32, &th, &dist, &near);
+    if (near) {
+      const unsigned long long slot = atomicAdd(fl.count, 1ULL);
+      if ((int64_t)slot < fl.cap) {
+        fl.pairs[2 * slot] = i;
+        fl.pairs[2 * slot + 1] = j;
+      }
+    }
+    /* set or clear: the word may hold a stale bit when a column is recomputed */
+    if (ok) atomicOr(g.bits + (size_t)i * g.stride32 + (j >> 5), 1u << (j & 31));
+    else atomicAnd(g.bits + (size_t)i * g.stride32 + (j >> 5), ~(1u << (j & 31)));
+  }
+  (void)E;
+}
+
+template <int D>
+static void launch_column(GroupView g, const double* aos, const double* soa, int j_begin, Shard sh, Thresholds th, Flagged fl,
+                          cudaStream_t st) {
+  constexpr int TW = 12;
+  const size_t smem = ((Rec<D>::N * 8 + 127) / 128) * 128 + (size_t)Rec<D>::E * TW * 32 * 8;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(pairwise_column_kernel<D, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  const int slabs = (g.n + 31) / 32;
+  dim3 grid((slabs + TW - 1) / TW, g.n - j_begin);
+  pairwise_column_kernel<D, TW><<<grid, TW * 32, smem, st>>>(g, aos, soa, j_begin, sh, th, fl);
+}
+
 static void gather_launch(int dim, GroupView g, const double* traj, int k0, double* aos, double* soa, cudaStream_t st) {
   if (k0 >= g.n) return;
   if (dim == 3) gather_records_kernel<3><<<g.n - k0, 160, 0, st>>>(g, traj, k0, aos, soa);
@@ -419,6 +487,13 @@ void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, co
   const int cb_begin = j_begin / 32;
   const int cb_end = (g.n + 31) / 32;
   dim3 grid((g.n + TILE_SEG - 1) / TILE_SEG, cb_end - cb_begin);
+  /* online case: a handful of new closures against a large group -> lanes over the older closures */
+  static const bool no_column = getenv("RPGO_NO_COLUMN_KERNEL") != nullptr;
+  if (g_tiled_variant == 6 && !no_column && g.n - j_begin <= 32 && j_begin >= 32) {
+    if (dim == 3) launch_column<3>(g, aos, soa, j_begin, sh, th, fl, st);
+    else launch_column<2>(g, aos, soa, j_begin, sh, th, fl, st);
+    return;
+  }
   /* few work items (small groups, or a handful of new columns in the online case): short row segments, so that the
    * launch fills the SMs and a block is 4 iterations long instead of 43 (latency of a single-closure update) */
   const long long items512 = (long long)((g.n + TILE_SEG - 1) / TILE_SEG) * (cb_end - cb_begin);

@@ -608,3 +608,33 @@ def test_find_inliers_batch_spread_over_ranks():
     for res in got:
         for (k, ids), (kb, ib) in zip(want, res):
             assert k == kb and ids.tolist() == ib.tolist()
+
+
+def test_online_column_kernel_equals_batch():
+    """a few closures appended one at a time to a large group (column-mode kernel: lanes over the older closures)
+    give the same adjacency, degrees, flagged pairs and inliers as one batch append (tiled kernel)"""
+    n0, extra = 5000, 5
+    gph = synth.config2(seed=13, P=5200, n=n0 + extra)
+    arr = synth.as_arrays(gph)
+    params = dict(odom_threshold=-1.0, lc_threshold=5.0)
+    a = PcmGpu(3, 0, **params)
+    b = PcmGpu(3, 0, **params)
+    for x in (a, b):
+        x.odom_append_arrays(arr["o_prev"], arr["o_new"], arr["o_pose"], arr["o_cov"], arr["o_init"])
+    a.lc_append_arrays(arr["l_from"], arr["l_to"], arr["l_pose"], arr["l_cov"])
+    b.lc_append_arrays(arr["l_from"][:n0], arr["l_to"][:n0], arr["l_pose"][:n0], arr["l_cov"][:n0])
+    for k in range(n0, n0 + extra - 2):
+        b.lc_append_arrays(arr["l_from"][k:k + 1], arr["l_to"][k:k + 1], arr["l_pose"][k:k + 1], arr["l_cov"][k:k + 1])
+    k = n0 + extra - 2
+    b.lc_append_arrays(arr["l_from"][k:], arr["l_to"][k:], arr["l_pose"][k:], arr["l_cov"][k:])   # two at once
+    assert np.array_equal(a.group_bits(0), b.group_bits(0))
+    assert np.array_equal(a.degrees(0), b.degrees(0))
+    fa, fb = a.flagged(0), b.flagged(0)
+    assert fa[0] == fb[0] and sorted(map(tuple, fa[1].tolist())) == sorted(map(tuple, fb[1].tolist()))
+    ka, ia, _ = a.find_inliers_raw(0, pkg.CLIQUE_HEU)
+    kb, ib, _ = b.find_inliers_raw(0, pkg.CLIQUE_HEU)
+    assert ka == kb and ia.tolist() == ib.tolist()
+    # recomputing the last columns in place must not change anything (set-or-clear stores)
+    b.recompute(0, n0 + extra - 3)
+    assert np.array_equal(a.group_bits(0), b.group_bits(0))
+    a.close(); b.close()
