@@ -107,7 +107,10 @@ class PcmGpu:
             a, b, n = self.group_info(g)
             if 0 < n <= 4096 and self.loop_check:
                 adj, _ = self.group_adj(g, with_dist=False)
-                np.savetxt(os.path.join(folder, "%s-%s_adj_matrix.txt" % (a, b)), adj, fmt="%d")
+                # keys without a symbol character have prefix '\0' (e.g. plain g2o ids): the reference's file name would
+                # then contain a NUL and the file is never created; the ordinal is written instead
+                name = lambda c: c if c.isprintable() and c not in "/\\" else str(ord(c))
+                np.savetxt(os.path.join(folder, "%s-%s_adj_matrix.txt" % (name(a), name(b))), adj, fmt="%d")
         with open(os.path.join(folder, "outlier_rejection_status.txt"), "a") as f:  # logSpinStatus
             f.write("%d %d %d %d\n" % (self.total_lc, self.total_good_lc, int(spin_s * 1e3), int(clique_s * 1e3)))
         with open(os.path.join(folder, "rpgo_status.csv"), "a") as f:  # RobustSolver::update

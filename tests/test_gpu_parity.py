@@ -1,11 +1,13 @@
 """GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
 Bit-exact for the adjacency bitset, the inlier ids and the trajectory cache; distances compared with ==."""
+import os
+
 import numpy as np
 import pytest
 
 import orc
 import scenarios
-from gpu_common import PcmGpu, pkg, synth
+from gpu_common import ROOT, PcmGpu, pkg, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -638,3 +640,26 @@ def test_online_column_kernel_equals_batch():
     b.recompute(0, n0 + extra - 3)
     assert np.array_equal(a.group_bits(0), b.group_bits(0))
     a.close(); b.close()
+
+
+def test_rpgo_read_g2o_cli(tmp_path):
+    """config 1 end to end through files: the `ordered` fixture written as g2o, run through tools/rpgo_read_g2o.py
+    (PcmSimple3D like examples/RpgoReadG2o.cpp), result.g2o + status logs read back.  Expected counts: SURVEY 8(d) config 1
+    (17 closures all kept at 1.0/1.0 -> 153 factors; 0.05/0.01 -> 16 inliers, 152 factors)."""
+    import importlib
+    import importlib.util
+    g2o = importlib.import_module("kimera-rpgo_b200.g2o")
+    values, edges = scenarios.g2o_fixture("ordered")
+    src = str(tmp_path / "ordered.g2o")
+    g2o.write_g2o(src, values, [(a, b, p, c) for _, a, b, p, c in edges], d=3)
+    spec = importlib.util.spec_from_file_location("rpgo_read_g2o", os.path.join(ROOT, "tools", "rpgo_read_g2o.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    for thr, n_fac, n_inl in [(("1.0", "1.0"), 153, 17), (("0.05", "0.01"), 152, 16)]:
+        out = str(tmp_path / ("out_%s" % thr[0]))
+        assert cli.main(["rpgo_read_g2o.py", "3d", src, thr[0], thr[1], out]) == 0
+        v2, e2 = g2o.load3d(os.path.join(out, "result.g2o"))
+        assert len(v2) == len(values) and len(e2) == n_fac
+        st = open(os.path.join(out, "outlier_rejection_status.txt")).read().splitlines()
+        assert st[0] == "total inliers spin-time mc-time" and [int(x) for x in st[1].split()[:2]] == [17, n_inl]
+        assert os.path.exists(os.path.join(out, "rpgo_status.csv"))
