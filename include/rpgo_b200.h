@@ -16,7 +16,9 @@
  * Conventions: plain C types only; all pointers are HOST pointers to caller-owned buffers unless a
  * name ends in _device; device memory is owned by the library; every function returns an int status
  * (RPGO_OK == 0) and never throws; a handle is single-threaded (one CUDA stream, one GPU).
- * There is no CPU fallback: rpgo_create fails with RPGO_ERR_CUDA when no sm_100 device is usable.
+ * There is no CPU fallback: rpgo_create fails with RPGO_ERR_CUDA when the selected device is not an sm_100 GPU.
+ * Every entry point switches to the handle's device for the duration of the call and restores the caller's current
+ * device; device memory comes from a library-private stream-ordered pool (the application's default pool is untouched).
  *
  * Data layout:
  *   key        uint64, gtsam::Key (gtsam::Symbol: chr = key >> 56, index = low 56 bits)
@@ -55,7 +57,11 @@ extern "C" {
 
 #define RPGO_KERNEL_AUTO 0
 #define RPGO_KERNEL_DIRECT 1  /* v0: one thread per pair, operands gathered from global memory */
-#define RPGO_KERNEL_TILED 2   /* TMA-staged shared-memory tiles */
+#define RPGO_KERNEL_TILED 2   /* TMA-staged shared-memory tiles (what AUTO selects) */
+/* cross-check forms of the tiled kernel, used by the parity tests only: one warp group with the straight-line pair
+ * function, and one warp group with the plain (branchy) pair function */
+#define RPGO_KERNEL_TILED_ONE_GROUP 24
+#define RPGO_KERNEL_TILED_V1 22
 
 typedef struct rpgo_handle rpgo_handle;
 
@@ -84,6 +90,9 @@ typedef struct rpgo_cfg {
 int rpgo_default_cfg(rpgo_cfg* cfg);
 int rpgo_create(const rpgo_cfg* cfg, rpgo_handle** out);
 void rpgo_destroy(rpgo_handle* h);
+/* back to the freshly created state (= a new Pcm object, Pcm.h:64-96), keeping stream, device arena, pinned staging and
+ * communicator: what a long-lived solver calls between independent graphs */
+int rpgo_reset(rpgo_handle* h);
 const char* rpgo_last_error(const rpgo_handle* h);
 /* block until all work queued on the handle's stream has finished */
 int rpgo_sync(rpgo_handle* h);
@@ -154,7 +163,8 @@ int rpgo_find_inliers_batch(rpgo_handle* h, int32_t n_groups, const int32_t* gro
                             const int64_t* n_new, const int64_t* prev_size, int32_t* ids_out, const int64_t* ids_offset,
                             int64_t* size_out);
 
-/* ---- multi-GPU inlier selection: candidate partition + incumbent exchange ------------------------------
+/* ---- multi-GPU inlier selection with a caller-provided collective -------------------------------------------
+ * Alternative to rpgo_comm_init for applications that cannot use NCCL (the gloo CPU tests do this).
  * With cfg.world > 1 and an exchange function registered, rpgo_find_inliers partitions the clique search's root
  * candidates over the ranks (candidate v belongs to rank v mod world in the heuristic, root n-1-v likewise in the
  * exact search) and calls `fn` on the host, on every rank in the same order, to combine the incumbent:
@@ -169,6 +179,26 @@ int rpgo_find_inliers_batch(rpgo_handle* h, int32_t n_groups, const int32_t* gro
 #define RPGO_XCHG_BCAST_I32 2
 typedef int (*rpgo_exchange_fn)(void* user, int32_t op, void* buf, int64_t count, int32_t root);
 int rpgo_set_exchange(rpgo_handle* h, rpgo_exchange_fn fn, void* user);
+
+/* ---- multi-GPU data plane behind the ABI (the reference, Pcm.h, is single-process) ---------------
+ * One process (or thread) per GPU, each with its own handle created with cfg.rank / cfg.world.  Rank 0 calls
+ * rpgo_comm_unique_id and hands the RPGO_COMM_ID_BYTES bytes to the other ranks by whatever means the application has
+ * (MPI, a file, torch.distributed's store); then every rank calls rpgo_comm_init, which builds an NCCL communicator over
+ * the handles' GPUs (collective call: all ranks must enter it).  From then on
+ *   - rpgo_lc_append computes only this rank's row chunks of every touched group and all-gathers the adjacency rows
+ *     with ncclAllGather / grouped ncclBroadcast on the handle's stream (NVLink / NVSwitch), so that every rank ends
+ *     with the full symmetric bitset and degrees;
+ *   - rpgo_find_inliers partitions the clique search's root candidates over the ranks and combines the incumbent with
+ *     ncclAllReduce; rpgo_find_inliers_batch spreads whole groups over the ranks;
+ *   - every rank returns identical results.
+ * Every rank must issue the same sequence of calls with the same data (the tables are replicated).
+ * NCCL is bound at run time (dlopen libnccl.so.2); rpgo_comm_init fails with RPGO_ERR_CUDA when it is not installed. */
+#define RPGO_COMM_ID_BYTES 128
+int rpgo_comm_unique_id(void* id_out);
+int rpgo_comm_init(rpgo_handle* h, const void* id, int32_t rank, int32_t world);
+int rpgo_comm_destroy(rpgo_handle* h);
+/* measurement hook: all-gather group g's row chunks and rebuild mirror + degrees (what rpgo_lc_append does after K3) */
+int rpgo_group_allgather(rpgo_handle* h, int32_t g);
 
 /* ---- N4: multi-robot frame alignment, the batched front half (Pcm::multirobotValueInitialization,
  * Pcm.h:1024-1055; the GNC pose averaging that follows stays on GTSAM) -------------------------------------
@@ -191,7 +221,8 @@ int rpgo_adj_bits_device(rpgo_handle* h, int32_t g, void** bits_device, int64_t*
 /* vertex degrees (popcount of each row) */
 int rpgo_degrees(rpgo_handle* h, int32_t g, int32_t* deg_out);
 /* pairs (i, j), i < j, whose distance lies within cfg.band of the threshold (the explicitly flagged
- * near-threshold set).  pairs_out holds up to cap pairs as 2 ints each; *n_out = total flagged. */
+ * near-threshold set).  pairs_out holds up to cap pairs as 2 ints each; *n_out = total flagged.  With a communicator
+ * (rows sharded over ranks) the call is collective and returns the union over the ranks. */
 int rpgo_near_threshold(rpgo_handle* h, int32_t g, int32_t* pairs_out, int64_t cap, int64_t* n_out);
 /* debug: recompute distances of all pairs of group g into an n x n row-major host matrix (small n only) */
 int rpgo_pair_distances(rpgo_handle* h, int32_t g, double* dist_out);
@@ -205,6 +236,8 @@ int rpgo_group_pairwise(rpgo_handle* h, int32_t g, int64_t j_begin);
 /* multi-GPU: after the caller has all-gathered the upper-triangle row chunks, rebuild the lower
  * triangle and the degrees on this GPU */
 int rpgo_group_finalize(rpgo_handle* h, int32_t g);
+/* one bitset pass alone, for bandwidth measurements: which = 0 mirror (lower triangle from the upper one), 1 degrees */
+int rpgo_debug_pass(rpgo_handle* h, int32_t g, int32_t which);
 /* row-chunk geometry of group g for the all-gather: rows are cut into 2*world chunks of chunk_rows rows */
 int rpgo_group_chunking(rpgo_handle* h, int32_t g, int64_t* chunk_rows, int64_t* padded_rows);
 /* number of kernels this handle has launched since creation */

@@ -30,6 +30,7 @@ SYMBOLS = [
     ("rpgo_default_cfg", C.c_int, [C.POINTER(RpgoCfg)]),
     ("rpgo_create", C.c_int, [C.POINTER(RpgoCfg), C.POINTER(C.c_void_p)]),
     ("rpgo_destroy", None, [C.c_void_p]),
+    ("rpgo_reset", C.c_int, [C.c_void_p]),
     ("rpgo_last_error", C.c_char_p, [C.c_void_p]),
     ("rpgo_sync", C.c_int, [C.c_void_p]),
     ("rpgo_stream", C.c_void_p, [C.c_void_p]),
@@ -45,6 +46,10 @@ SYMBOLS = [
     ("rpgo_find_inliers", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, c_i32p, c_i64p, c_i32p]),
     ("rpgo_find_inliers_batch", C.c_int, [C.c_void_p, C.c_int32, c_i32p, C.c_int32, c_i64p, c_i64p, c_i32p, c_i64p, c_i64p]),
     ("rpgo_set_exchange", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("rpgo_comm_unique_id", C.c_int, [C.c_void_p]),
+    ("rpgo_comm_init", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    ("rpgo_comm_destroy", C.c_int, [C.c_void_p]),
+    ("rpgo_group_allgather", C.c_int, [C.c_void_p, C.c_int32]),
     ("rpgo_frame_align_measurements", C.c_int, [C.c_void_p, C.c_int32, C.c_uint8, C.c_int64, c_i32p, c_dp]),
     ("rpgo_robot_odom_values", C.c_int, [C.c_void_p, C.c_uint8, c_dp, C.c_int64, c_u64p, c_dp, c_i64p]),
     ("rpgo_adj_bits", C.c_int, [C.c_void_p, C.c_int32, c_u64p, C.c_int64]),
@@ -55,6 +60,7 @@ SYMBOLS = [
     ("rpgo_group_recompute", C.c_int, [C.c_void_p, C.c_int32, C.c_int64]),
     ("rpgo_group_pairwise", C.c_int, [C.c_void_p, C.c_int32, C.c_int64]),
     ("rpgo_group_finalize", C.c_int, [C.c_void_p, C.c_int32]),
+    ("rpgo_debug_pass", C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     ("rpgo_group_chunking", C.c_int, [C.c_void_p, C.c_int32, c_i64p, c_i64p]),
     ("rpgo_launch_count", C.c_int64, [C.c_void_p]),
     ("rpgo_fp64_peak", C.c_int, [C.c_int32, c_dp]),
@@ -65,6 +71,7 @@ SYMBOLS = [
 
 EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32)
 XCHG_MIN_I64, XCHG_MAX_I64, XCHG_BCAST_I32 = 0, 1, 2
+COMM_ID_BYTES = 128
 
 _lib = None
 

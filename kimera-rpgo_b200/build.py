@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librpgo_b200.so")
-SOURCES = ["capi.cu", "pcm_kernels.cu", "pcm_tiled.cu", "clique_kernels.cu", "clique_exact.cu"]
+SOURCES = ["capi.cu", "comm.cu", "pcm_kernels.cu", "pcm_tiled.cu", "clique_kernels.cu", "clique_exact.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-fmad=false",  # numerical contract: no implicit contraction; fused ops are explicit fma() calls
@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    subprocess.check_call(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart"])
+    subprocess.check_call(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart", "-ldl"])
     return LIB
 
 

@@ -17,6 +17,7 @@
 #include <ctime>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <set>
 #include <atomic>
 #include <climits>
@@ -26,31 +27,62 @@
 #include <vector>
 
 #include "../../include/rpgo_b200.h"
+#include "comm.h"
 #include "kernels.cuh"
 
 using namespace rpgo;
 
 namespace {
 
-/* Device memory comes from a per-handle bump arena whose chunks are taken from CUDA's stream-ordered pool
- * (cudaMallocAsync; the pool keeps freed chunks cached, so the next handle of the process re-uses them):
- * a PCM session makes hundreds of small growing allocations (36 groups x 10 arrays) and plain cudaMalloc
- * costs milliseconds each on this platform. */
+/* Device memory comes from a per-handle bump arena whose chunks are taken from a stream-ordered memory pool that is
+ * PRIVATE to this library (one per device, created on first use, never trimmed: freed chunks stay cached, so the next
+ * handle of the process re-uses them).  A PCM session makes hundreds of small growing allocations (36 groups x 10
+ * arrays) and plain cudaMalloc costs milliseconds each on this platform.  The application's default pool is not
+ * touched. */
+constexpr int MAX_DEVICES = 64;
+cudaMemPool_t library_pool(int dev) {
+  static std::mutex mu;
+  static cudaMemPool_t pools[MAX_DEVICES] = {}; /* intentionally never destroyed (no CUDA calls at process exit) */
+  if (dev < 0 || dev >= MAX_DEVICES) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!pools[dev]) {
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool = nullptr;
+    if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    uint64_t thr = ~0ULL;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    pools[dev] = pool;
+  }
+  return pools[dev];
+}
+
 struct Arena {
   struct Chunk { char* p; size_t cap, used; };
   std::vector<Chunk> chunks;
   cudaStream_t st = nullptr;
+  cudaMemPool_t pool = nullptr;
   static constexpr size_t CHUNK = (size_t)64 << 20;
   void* alloc(size_t bytes) {
     bytes = (bytes + 255) & ~size_t(255);
-    if (!chunks.empty() && chunks.back().used + bytes <= chunks.back().cap) {
-      void* r = chunks.back().p + chunks.back().used;
-      chunks.back().used += bytes;
-      return r;
+    for (size_t i = chunks.size(); i-- > 0;) { /* newest first; older chunks have room again after rewind() */
+      Chunk& c = chunks[i];
+      if (c.used + bytes <= c.cap) {
+        void* r = c.p + c.used;
+        c.used += bytes;
+        return r;
+      }
     }
     const size_t cap = bytes > CHUNK ? bytes : CHUNK;
     void* p = nullptr;
-    if (cudaMallocAsync(&p, cap, st) != cudaSuccess) {
+    if (cudaMallocFromPoolAsync(&p, cap, pool, st) != cudaSuccess) {
       cudaGetLastError();
       return nullptr;
     }
@@ -63,6 +95,10 @@ struct Arena {
   void release() {
     for (auto& c : chunks) cudaFreeAsync(c.p, st);
     chunks.clear();
+  }
+  /* rpgo_reset: every block handed out so far is dead; keep the chunks */
+  void rewind() {
+    for (auto& c : chunks) c.used = 0;
   }
 };
 
@@ -92,16 +128,77 @@ struct DevBuf {
   T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+/* Pinned host staging.  cudaHostAlloc costs ~10 ms for the 44 MB a 50k-closure batch needs, so buffers are recycled
+ * through a process-wide free list: a handle borrows one and hands it back when it is destroyed.  Nothing here runs a
+ * CUDA call from a static or thread_local destructor (the list itself is leaked at exit on purpose). */
+struct PinCache {
+  std::mutex mu;
+  std::vector<std::pair<void*, size_t>> free_list;
+};
+PinCache& pin_cache() {
+  static PinCache* c = new PinCache();
+  return *c;
+}
 struct PinBuf {
   void* p = nullptr;
   size_t cap = 0;
-  ~PinBuf() { if (p) cudaFreeHost(p); }
+  void give_back() {
+    if (!p) return;
+    PinCache& c = pin_cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    c.free_list.push_back({p, cap});
+    p = nullptr;
+    cap = 0;
+  }
   void* ensure(size_t bytes) {
     if (bytes <= cap) return p;
-    if (p) cudaFreeHost(p);
-    cap = std::max(bytes, cap * 2);
-    if (cudaMallocHost(&p, cap) != cudaSuccess) { p = nullptr; cap = 0; }
+    give_back();
+    PinCache& c = pin_cache();
+    {
+      std::lock_guard<std::mutex> lk(c.mu);
+      int best = -1;
+      for (int i = 0; i < (int)c.free_list.size(); ++i)
+        if (c.free_list[i].second >= bytes && (best < 0 || c.free_list[i].second < c.free_list[best].second)) best = i;
+      if (best >= 0) {
+        p = c.free_list[best].first;
+        cap = c.free_list[best].second;
+        c.free_list.erase(c.free_list.begin() + best);
+        return p;
+      }
+      /* nothing fits: drop the largest cached buffer so that growing sessions do not pile up stale ones */
+      if (!c.free_list.empty()) {
+        int big = 0;
+        for (int i = 1; i < (int)c.free_list.size(); ++i)
+          if (c.free_list[i].second > c.free_list[big].second) big = i;
+        cudaFreeHost(c.free_list[big].first);
+        c.free_list.erase(c.free_list.begin() + big);
+      }
+    }
+    size_t want = (bytes + (bytes >> 2) + 4095) & ~size_t(4095);
+    if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+      cap = 0;
+      return nullptr;
+    }
+    cap = want;
     return p;
+  }
+};
+
+/* every entry point runs on the handle's device and leaves the caller's current device as it found it */
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) {
+      cudaSetDevice(dev);
+      switched = true;
+    }
+  }
+  ~DeviceGuard() {
+    if (switched && prev >= 0) cudaSetDevice(prev);
   }
 };
 
@@ -127,11 +224,6 @@ struct Group {
 
 constexpr int64_t FLAG_CAP = 1 << 20;
 
-PinBuf& pinned_staging() {
-  static thread_local PinBuf buf;
-  return buf;
-}
-
 }  // namespace
 
 static constexpr int64_t CLIQUE_BLOCKS = 148 * 8;
@@ -150,6 +242,9 @@ struct CliqueWorker {
 struct rpgo_handle {
   Arena arena;
   rpgo_cfg cfg;
+  int device = 0;               /* CUDA ordinal this handle lives on (every entry point switches to it) */
+  rpgo::Comm* comm = nullptr;   /* NCCL communicator over the world's GPUs (rpgo_comm_init), or null */
+  PinBuf pin;                   /* pinned host staging, borrowed from the process-wide cache */
   int dim = 3, mode = 0, E = 50, PS = 12, NN = 36;
   bool odom_check = true, loop_check = true;
   Thresholds th;
@@ -172,7 +267,6 @@ struct rpgo_handle {
   std::map<std::pair<uint8_t, uint8_t>, int32_t> gindex;
   std::map<uint64_t, int32_t> lindex; /* landmark key -> group ordinal */
 
-  /* staging (the pinned host buffer is per thread, shared by successive handles: cudaMallocHost is slow) */
   DevBuf d_stage;
   DevBuf d_lcent, d_ok, d_dist, d_scan;
   /* clique scratch: one set for the single-group entry point, one per worker of the batched one */
@@ -185,6 +279,10 @@ struct rpgo_handle {
       b->arena = &arena;
   }
   ~rpgo_handle() {
+    DeviceGuard dg(device);
+    if (stream) cudaStreamSynchronize(stream);
+    if (comm) rpgo::comm_destroy(comm);
+    pin.give_back();
     for (CliqueWorker* w : workers) {
       if (w->stream) {
         cudaStreamSynchronize(w->stream);
@@ -307,26 +405,21 @@ static int run_pairwise(rpgo_handle* h, Group* g, int64_t j_begin, double* dist_
   }
   Shard sh = group_shard(h, g);
   int kernel = h->cfg.kernel;
-  {
-    extern int g_direct_minb_set(int);
-    extern int g_tiled_variant_set(int);
-    g_direct_minb_set(kernel == 13 ? 3 : kernel == 14 ? 4 : 2);
-    if (kernel == 13 || kernel == 14) kernel = RPGO_KERNEL_DIRECT;
-    g_tiled_variant_set(kernel >= 20 && kernel <= 35 ? kernel - 20 : 6);
-    if (kernel >= 20 && kernel <= 35) kernel = RPGO_KERNEL_TILED;
-  }
+  int variant = 0;
+  if (kernel == RPGO_KERNEL_TILED_ONE_GROUP) { variant = 1; kernel = RPGO_KERNEL_TILED; }
+  else if (kernel == RPGO_KERNEL_TILED_V1) { variant = 2; kernel = RPGO_KERNEL_TILED; }
   if (dist_dev) kernel = RPGO_KERNEL_DIRECT;
-  if (kernel == RPGO_KERNEL_AUTO) kernel = (h->mode == MODE_PCM) ? RPGO_KERNEL_TILED : RPGO_KERNEL_DIRECT;
+  if (kernel == RPGO_KERNEL_AUTO) kernel = RPGO_KERNEL_TILED;
   if (kernel == RPGO_KERNEL_TILED && h->mode != MODE_PCM) kernel = RPGO_KERNEL_DIRECT;
   if (kernel == RPGO_KERNEL_TILED) {
     if (g->gathered < g->n) {
-      launch_gather_records(h->dim, v, h->traj.as<double>(), (int)g->gathered, g->rec_aos.as<double>(), g->rec_soa.as<double>(),
-                            h->stream);
+      launch_gather_records(h->dim, v, h->traj.as<double>(), (int)g->gathered, g->rec_aos.as<double>(),
+                            g->rec_soa.as<double>(), h->stream);
       g->gathered = g->n;
       h->launches += 1;
     }
     launch_pairwise_tiled(h->dim, h->mode, v, g->rec_aos.as<double>(), g->rec_soa.as<double>(), (int)j_begin, sh, h->th,
-                          group_flagged(g), h->stream);
+                          group_flagged(g), variant, h->stream);
   } else
     launch_pairwise_direct(h->dim, h->mode, v, h->traj.as<double>(), (int)j_begin, sh, h->th, group_flagged(g), dist_dev,
                            h->stream);
@@ -341,6 +434,44 @@ static int finalize_group(rpgo_handle* h, Group* g, int64_t j_begin) {
   launch_degree(g->bits.as<uint32_t>(), g->stride32, (int)g->n, g->deg.as<int32_t>(), h->stream);
   h->launches += 2;
   H_CHECK_CUDA(h, cudaGetLastError());
+  return RPGO_OK;
+}
+
+int rpgo::CliqueShard::xchg(int32_t op, void* buf, int64_t count, int32_t root) const {
+  if (comm) {
+    switch (op) {
+      case RPGO_XCHG_MIN_I64: return comm_allreduce_i64_host(comm, (long long*)buf, (size_t)count, false, comm_stream);
+      case RPGO_XCHG_MAX_I64: return comm_allreduce_i64_host(comm, (long long*)buf, (size_t)count, true, comm_stream);
+      case RPGO_XCHG_BCAST_I32: return comm_bcast_host(comm, buf, (size_t)count * 4, root, comm_stream);
+      default: return 1;
+    }
+  }
+  if (exchange) return exchange(user, op, buf, count, root);
+  return 1;
+}
+
+static CliqueShard clique_shard(rpgo_handle* h, cudaStream_t st) {
+  CliqueShard cs;
+  cs.rank = h->cfg.rank;
+  cs.world = h->cfg.world;
+  cs.exchange = h->xchg;
+  cs.user = h->xchg_user;
+  cs.comm = h->comm;
+  cs.comm_stream = st;
+  return cs;
+}
+
+/* the one exchange step of the sharded pair matrix: all-gather of this group's adjacency row chunks over NCCL, in place,
+ * on the handle's stream (every rank holds the same group geometry: the tables are replicated) */
+static int allgather_group(rpgo_handle* h, Group* g) {
+  if (!h->comm) { h->err = "no communicator: call rpgo_comm_init first"; return RPGO_ERR_INVALID; }
+  if ((!h->loop_check && !g->landmark) || g->n < 1 || !g->bits.p) return RPGO_OK;
+  const Shard s = group_shard(h, g);
+  const size_t chunk_bytes = (size_t)s.chunk_rows * (size_t)g->stride32 * 4;
+  if (comm_allgather_row_chunks(h->comm, g->bits.p, chunk_bytes, h->stream) != 0) {
+    h->err = std::string("adjacency all-gather failed: ") + comm_error(h->comm);
+    return RPGO_ERR_CUDA;
+  }
   return RPGO_OK;
 }
 
@@ -376,13 +507,23 @@ int rpgo_create(const rpgo_cfg* cfg, rpgo_handle** out) {
   if ((cfg->dim != 2 && cfg->dim != 3) || (cfg->mode != 0 && cfg->mode != 1)) return RPGO_ERR_INVALID;
   if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return RPGO_ERR_INVALID;
   int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return RPGO_ERR_CUDA; /* no CPU fallback */
-  if (cfg->device >= 0) {
-    if (cfg->device >= ndev) return RPGO_ERR_INVALID;
-    if (cudaSetDevice(cfg->device) != cudaSuccess) return RPGO_ERR_CUDA;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return RPGO_ERR_CUDA; } /* no CPU fallback */
+  int dev = cfg->device;
+  if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) return RPGO_ERR_CUDA;
+  if (dev >= ndev || dev >= MAX_DEVICES) return RPGO_ERR_INVALID;
+  {
+    /* the library carries sm_100a code only: refuse anything else instead of failing at the first launch */
+    int major = 0, minor = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess)
+      return RPGO_ERR_CUDA;
+    if (major != 10 || minor != 0) return RPGO_ERR_CUDA;
   }
+  DeviceGuard dg(dev);
   rpgo_handle* h = new rpgo_handle();
+  h->device = dev;
   h->cfg = *cfg;
+  h->cfg.device = dev;
   if (h->cfg.band <= 0) h->cfg.band = 1e-9;
   if (h->cfg.scan_chunk <= 0) h->cfg.scan_chunk = 64;
   h->dim = cfg->dim;
@@ -400,7 +541,13 @@ int rpgo_create(const rpgo_cfg* cfg, rpgo_handle** out) {
   h->th.dist_trans = cfg->dist_trans_threshold;
   h->th.dist_rot = cfg->dist_rot_threshold;
   h->th.band = h->cfg.band;
+  h->arena.pool = library_pool(dev);
+  if (!h->arena.pool) {
+    delete h;
+    return RPGO_ERR_CUDA;
+  }
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    h->stream = nullptr;
     delete h;
     return RPGO_ERR_CUDA;
   }
@@ -408,16 +555,6 @@ int rpgo_create(const rpgo_cfg* cfg, rpgo_handle** out) {
   if (cudaEventCreateWithFlags(&h->ev_stage, cudaEventDisableTiming) != cudaSuccess) {
     delete h;
     return RPGO_ERR_CUDA;
-  }
-  {
-    /* keep freed arena chunks cached in the device's default pool across handles */
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      uint64_t thr = ~0ULL;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
   }
   /* entry 0 = default T: identity pose, zero covariance, node 0, rotation_info true */
   if (h->traj.ensure((size_t)1024 * h->E * sizeof(double), 0, h->stream) != cudaSuccess) {
@@ -436,14 +573,51 @@ int rpgo_create(const rpgo_cfg* cfg, rpgo_handle** out) {
 
 void rpgo_destroy(rpgo_handle* h) {
   if (!h) return;
-  cudaStreamSynchronize(h->stream);
-  delete h;
+  delete h; /* ~rpgo_handle switches to the handle's device, drains the stream and tears the communicator down */
+}
+
+/* Back to the state right after rpgo_create (a freshly constructed Pcm object, Pcm.h:64-96) while keeping what is
+ * expensive to build: the stream(s), the device arena's memory, the pinned staging buffer and the communicator. */
+int rpgo_reset(rpgo_handle* h) {
+  if (!h) return RPGO_ERR_INVALID;
+  DeviceGuard dg(h->device);
+  H_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (CliqueWorker* w : h->workers) H_CHECK_CUDA(h, cudaStreamSynchronize(w->stream));
+  for (Group* g : h->groups) delete g;
+  h->groups.clear();
+  h->gindex.clear();
+  h->lindex.clear();
+  h->key2idx.clear();
+  h->prefixes.clear();
+  h->missing_refs.clear();
+  h->traj_dirty = false;
+  for (DevBuf* b : {&h->traj, &h->d_stage, &h->d_lcent, &h->d_ok, &h->d_dist, &h->d_scan, &h->cset.degmask, &h->cset.picks,
+                    &h->cset.elim, &h->cset.result, &h->cset.ctl, &h->cset.rwork}) {
+    b->p = nullptr;
+    b->cap = 0;
+  }
+  for (CliqueWorker* w : h->workers)
+    for (DevBuf* b : {&w->set.degmask, &w->set.picks, &w->set.elim, &w->set.result, &w->set.ctl, &w->set.rwork}) {
+      b->p = nullptr;
+      b->cap = 0;
+    }
+  h->arena.rewind();
+  H_CHECK_CUDA(h, h->traj.ensure((size_t)1024 * h->E * sizeof(double), 0, h->stream));
+  std::vector<double> e0(h->E, 0.0);
+  if (h->dim == 3) { e0[0] = e0[4] = e0[8] = 1.0; e0[Dim<3>::OFF_ROT] = 1.0; }
+  else { e0[0] = 1.0; e0[Dim<2>::OFF_ROT] = 1.0; }
+  H_CHECK_CUDA(h, cudaMemcpyAsync(h->traj.p, e0.data(), sizeof(double) * h->E, cudaMemcpyHostToDevice, h->stream));
+  H_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->traj_n = 1;
+  h->err.clear();
+  return RPGO_OK;
 }
 
 const char* rpgo_last_error(const rpgo_handle* h) { return h ? h->err.c_str() : "null handle"; }
 
 int rpgo_sync(rpgo_handle* h) {
   if (!h) return RPGO_ERR_INVALID;
+  DeviceGuard dg(h->device);
   H_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
   return RPGO_OK;
 }
@@ -456,6 +630,7 @@ int64_t rpgo_traj_size(rpgo_handle* h) { return h ? (int64_t)h->key2idx.size() :
 int rpgo_odom_append(rpgo_handle* h, int64_t n, const uint64_t* prev_key, const uint64_t* new_key,
                      const double* delta_pose, const double* delta_cov, const double* init_pose) {
   if (!h || n < 0) return RPGO_ERR_INVALID;
+  DeviceGuard dg(h->device);
   if (n == 0) return RPGO_OK;
   if (!prev_key || !new_key || !delta_pose || !delta_cov) return RPGO_ERR_INVALID;
   const int E = h->E, PS = h->PS, NN = h->NN;
@@ -541,7 +716,7 @@ int rpgo_odom_append(rpgo_handle* h, int64_t n, const uint64_t* prev_key, const 
   const size_t bytes_pose = (size_t)n * PS * 8, bytes_cov = (size_t)n * NN * 8;
   const size_t off_cov = bytes_pose, off_out = off_cov + bytes_cov, off_chain = off_out + (size_t)n * 4;
   const size_t total = off_chain + chains.size() * sizeof(FoldChain) + 64;
-  char* pin = (char*)pinned_staging().ensure(total);
+  char* pin = (char*)h->pin.ensure(total);
   if (!pin) { h->err = "pinned staging allocation failed"; return RPGO_ERR_NOMEM; }
   double* p_pose = (double*)pin;
   double* p_cov = (double*)(pin + off_cov);
@@ -622,6 +797,7 @@ int rpgo_odom_append(rpgo_handle* h, int64_t n, const uint64_t* prev_key, const 
 
 int rpgo_traj_get(rpgo_handle* h, uint64_t key, double* pose, double* cov, int32_t* node, int32_t* rot_info) {
   if (!h || !pose) return RPGO_ERR_INVALID;
+  DeviceGuard dg(h->device);
   auto it = h->key2idx.find(key);
   if (it == h->key2idx.end()) return RPGO_ERR_NOT_FOUND;
   std::vector<double> e(h->E);
@@ -643,6 +819,7 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
                    const double* pose, const double* cov, uint8_t* accepted, int32_t* group, int32_t* index,
                    double* odom_dist) {
   if (!h || n < 0) return RPGO_ERR_INVALID;
+  DeviceGuard dg(h->device);
   if (n == 0) return RPGO_OK;
   if (!key_from || !key_to || !pose || !cov) return RPGO_ERR_INVALID;
   const int E = h->E, PS = h->PS, NN = h->NN;
@@ -685,7 +862,7 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
   const size_t o_cov = (size_t)n * PS * 8, o_if = o_cov + (size_t)n * NN * 8, o_ib = o_if + (size_t)n * 4,
                o_ck = o_ib + (size_t)n * 4, o_dst = (o_ck + (size_t)n + 15) & ~size_t(15),
                total = o_dst + (size_t)n * 8;
-  char* pin = (char*)pinned_staging().ensure(total + (size_t)n * 9 + 64);
+  char* pin = (char*)h->pin.ensure(total + (size_t)n * 9 + 64);
   if (!pin) { h->err = "pinned staging allocation failed"; return RPGO_ERR_NOMEM; }
   memcpy(pin, pose, (size_t)n * PS * 8);
   memcpy(pin + o_cov, cov, (size_t)n * NN * 8);
@@ -811,7 +988,12 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
     if (h->cfg.world <= 1) {
       rc = finalize_group(h, g, kv.second);
       if (rc != RPGO_OK) return rc;
-    }
+    } else if (h->comm) {
+      /* sharded rows: every rank computed its chunks; exchange them and rebuild mirror + degrees everywhere */
+      rc = allgather_group(h, g);
+      if (rc == RPGO_OK) rc = finalize_group(h, g, 0);
+      if (rc != RPGO_OK) return rc;
+    } /* else: the caller runs its own all-gather (rpgo_adj_bits_device) and then rpgo_group_finalize */
   }
   H_CHECK_CUDA(h, cudaGetLastError());
   mark("K3 + finalize launches");
@@ -823,6 +1005,7 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
 int rpgo_landmark_append(rpgo_handle* h, uint64_t landmark_key, int64_t n, const uint64_t* pose_key, const double* pose,
                          const double* cov, int32_t reset, int32_t* group_out) {
   if (!h || n < 0) return RPGO_ERR_INVALID;
+  DeviceGuard dg(h->device);
   if (n > 0 && (!pose_key || !pose || !cov)) return RPGO_ERR_INVALID;
   const int E = h->E, PS = h->PS, NN = h->NN;
   cudaStream_t st = h->stream;
@@ -873,7 +1056,7 @@ int rpgo_landmark_append(rpgo_handle* h, uint64_t landmark_key, int64_t n, const
   /* stage raw pose | cov, run the factor constructor (no odometry check), scatter into the group */
   const size_t o_cov = (size_t)n * PS * 8, o_if = o_cov + (size_t)n * NN * 8, o_ck = o_if + (size_t)n * 4,
                o_dst = (o_ck + (size_t)n + 15) & ~size_t(15), total = o_dst + (size_t)n * 8;
-  char* pin = (char*)pinned_staging().ensure(total + 64);
+  char* pin = (char*)h->pin.ensure(total + 64);
   if (!pin) { h->err = "pinned staging allocation failed"; return RPGO_ERR_NOMEM; }
   memcpy(pin, pose, (size_t)n * PS * 8);
   memcpy(pin + o_cov, cov, (size_t)n * NN * 8);
@@ -939,6 +1122,7 @@ int32_t rpgo_find_group(rpgo_handle* h, uint8_t id1, uint8_t id2) {
 
 int rpgo_lc_remove_last(rpgo_handle* h, int32_t gi, uint64_t* key_from, uint64_t* key_to) {
   if (!h || gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
+  DeviceGuard dg(h->device);
   Group* g = h->groups[gi];
   if (g->n <= 0 || g->landmark) return RPGO_ERR_NOT_FOUND; /* the reference never removes landmark observations */
   if (key_from) *key_from = g->kfrom.back();
@@ -1009,17 +1193,14 @@ static cudaError_t ensure_clique_set(CliqueSet* c, int n, cudaStream_t st) {
 int rpgo_find_inliers(rpgo_handle* h, int32_t gi, int32_t clique_mode, int64_t n_new, int64_t prev_size,
                       int32_t* ids_out, int64_t* size_out, int32_t* true_clique_out) {
   if (!h || !ids_out || !size_out) return RPGO_ERR_INVALID;
+  DeviceGuard dg(h->device);
   if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
   Group* g = h->groups[gi];
   const int n = (int)g->n;
   if (n <= 0 || (!h->loop_check && !g->landmark)) { h->err = "find_inliers: empty group or loop check disabled"; return RPGO_ERR_INVALID; }
   cudaStream_t st = h->stream;
   H_CHECK_CUDA(h, ensure_clique_set(&h->cset, n, st));
-  CliqueShard cs;
-  cs.rank = h->cfg.rank;
-  cs.world = h->cfg.world;
-  cs.exchange = h->xchg;
-  cs.user = h->xchg_user;
+  const CliqueShard cs = clique_shard(h, st);
   return run_clique(h, g, clique_mode, n_new, prev_size, &h->cset, st, cs, ids_out, size_out, true_clique_out, &h->launches,
                     &h->err);
 }
@@ -1032,6 +1213,7 @@ int rpgo_find_inliers_batch(rpgo_handle* h, int32_t n_groups, const int32_t* gro
                             const int64_t* n_new, const int64_t* prev_size, int32_t* ids_out, const int64_t* ids_offset,
                             int64_t* size_out) {
   if (!h || n_groups < 0 || (n_groups > 0 && (!groups || !ids_out || !ids_offset || !size_out))) return RPGO_ERR_INVALID;
+  DeviceGuard dg(h->device);
   if (n_groups == 0) return RPGO_OK;
   int max_n = 0;
   for (int k = 0; k < n_groups; ++k) {
@@ -1040,7 +1222,8 @@ int rpgo_find_inliers_batch(rpgo_handle* h, int32_t n_groups, const int32_t* gro
     if (g->n <= 0 || (!h->loop_check && !g->landmark)) { h->err = "find_inliers_batch: empty group or loop check disabled"; return RPGO_ERR_INVALID; }
     max_n = std::max<int>(max_n, (int)g->n);
   }
-  const bool spread = h->cfg.world > 1 && h->xchg != nullptr;
+  const CliqueShard all = clique_shard(h, h->stream);
+  const bool spread = all.active();
   const int world = spread ? h->cfg.world : 1, rank = spread ? h->cfg.rank : 0;
   /* workers: bounded by the scratch they need (the pick logs are CLIQUE_BLOCKS x n ints each) */
   const size_t per_set = (size_t)CLIQUE_BLOCKS * max_n * 4 + (size_t)max_n * 16;
@@ -1066,10 +1249,9 @@ int rpgo_find_inliers_batch(rpgo_handle* h, int32_t n_groups, const int32_t* gro
   std::vector<int> rcs(T, RPGO_OK);
   std::vector<std::string> errs(T);
   std::vector<int64_t> launches(T, 0);
-  int dev = 0;
-  cudaGetDevice(&dev);
+  const int dev = h->device;
   auto body = [&](int t) {
-    cudaSetDevice(dev);
+    cudaSetDevice(dev); /* worker threads start on device 0 */
     CliqueWorker* w = h->workers[t];
     for (;;) {
       const int q = next.fetch_add(1);
@@ -1104,7 +1286,7 @@ int rpgo_find_inliers_batch(rpgo_handle* h, int32_t n_groups, const int32_t* gro
       for (int64_t i = 0; i < cap; ++i)
         buf.push_back(mine && i < std::max<int64_t>(size_out[k], 0) ? (long long)ids_out[ids_offset[k] + i] : LLONG_MIN);
     }
-    if (h->xchg(h->xchg_user, RPGO_XCHG_MAX_I64, buf.data(), (int64_t)buf.size(), 0) != 0) { h->err = "exchange failed"; return RPGO_ERR_CUDA; }
+    if (all.xchg(RPGO_XCHG_MAX_I64, buf.data(), (int64_t)buf.size(), 0) != 0) { h->err = "exchange failed"; return RPGO_ERR_CUDA; }
     size_t pos = 0;
     for (int k = 0; k < n_groups; ++k) {
       const int64_t cap = h->groups[groups[k]]->n;
@@ -1123,9 +1305,59 @@ int rpgo_set_exchange(rpgo_handle* h, rpgo_exchange_fn fn, void* user) {
   return RPGO_OK;
 }
 
+/* ---- multi-GPU data plane (NCCL behind the ABI) -------------------------------------------------- */
+int rpgo_comm_unique_id(void* id_out) {
+  if (!id_out) return RPGO_ERR_INVALID;
+  std::string err;
+  if (comm_unique_id(id_out, &err) != 0) {
+    fprintf(stderr, "rpgo_comm_unique_id: %s\n", err.c_str());
+    return RPGO_ERR_CUDA;
+  }
+  return RPGO_OK;
+}
+
+int rpgo_comm_init(rpgo_handle* h, const void* id, int32_t rank, int32_t world) {
+  if (!h || !id) return RPGO_ERR_INVALID;
+  DeviceGuard dg(h->device);
+  if (rank != h->cfg.rank || world != h->cfg.world || world < 2) {
+    h->err = "rpgo_comm_init: rank/world must equal the handle's cfg.rank/cfg.world (world >= 2)";
+    return RPGO_ERR_INVALID;
+  }
+  if (h->comm) { comm_destroy(h->comm); h->comm = nullptr; }
+  std::string err;
+  if (comm_create(&h->comm, id, rank, world, &err) != 0) {
+    h->err = "rpgo_comm_init: " + err;
+    h->comm = nullptr;
+    return RPGO_ERR_CUDA;
+  }
+  return RPGO_OK;
+}
+
+int rpgo_comm_destroy(rpgo_handle* h) {
+  if (!h) return RPGO_ERR_INVALID;
+  DeviceGuard dg(h->device);
+  if (h->comm) {
+    cudaStreamSynchronize(h->stream);
+    comm_destroy(h->comm);
+    h->comm = nullptr;
+  }
+  return RPGO_OK;
+}
+
+int rpgo_group_allgather(rpgo_handle* h, int32_t gi) {
+  if (!h) return RPGO_ERR_INVALID;
+  DeviceGuard dg(h->device);
+  if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
+  if (h->cfg.world <= 1) return finalize_group(h, h->groups[gi], 0);
+  int rc = allgather_group(h, h->groups[gi]);
+  if (rc == RPGO_OK) rc = finalize_group(h, h->groups[gi], 0);
+  return rc;
+}
+
 /* ---------------------------------------------------------------------------------------------- */
 int rpgo_adj_bits(rpgo_handle* h, int32_t gi, uint64_t* rows_out, int64_t stride_words) {
   if (!h || !rows_out) return RPGO_ERR_INVALID;
+  DeviceGuard dg(h->device);
   if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
   Group* g = h->groups[gi];
   const int64_t n = g->n;
@@ -1151,6 +1383,7 @@ int rpgo_adj_bits_device(rpgo_handle* h, int32_t gi, void** bits_device, int64_t
 
 int rpgo_degrees(rpgo_handle* h, int32_t gi, int32_t* deg_out) {
   if (!h || !deg_out) return RPGO_ERR_INVALID;
+  DeviceGuard dg(h->device);
   if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
   Group* g = h->groups[gi];
   if (g->n == 0) return RPGO_OK;
@@ -1161,24 +1394,61 @@ int rpgo_degrees(rpgo_handle* h, int32_t gi, int32_t* deg_out) {
 
 int rpgo_near_threshold(rpgo_handle* h, int32_t gi, int32_t* pairs_out, int64_t cap, int64_t* n_out) {
   if (!h || !n_out) return RPGO_ERR_INVALID;
+  DeviceGuard dg(h->device);
   if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
   Group* g = h->groups[gi];
   *n_out = 0;
-  if (!g->fl_count.p) return RPGO_OK;
   unsigned long long c = 0;
-  H_CHECK_CUDA(h, cudaMemcpyAsync(&c, g->fl_count.p, 8, cudaMemcpyDeviceToHost, h->stream));
-  H_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
-  *n_out = (int64_t)c;
-  const int64_t m = std::min<int64_t>(std::min<int64_t>((int64_t)c, cap), FLAG_CAP);
-  if (pairs_out && m > 0) {
-    H_CHECK_CUDA(h, cudaMemcpyAsync(pairs_out, g->fl_pairs.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (g->fl_count.p) {
+    H_CHECK_CUDA(h, cudaMemcpyAsync(&c, g->fl_count.p, 8, cudaMemcpyDeviceToHost, h->stream));
     H_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  const int64_t mine = std::min<int64_t>((int64_t)c, FLAG_CAP);
+  if (!(h->cfg.world > 1 && h->comm)) {
+    *n_out = (int64_t)c;
+    const int64_t m = std::min<int64_t>(mine, cap);
+    if (pairs_out && m > 0) {
+      H_CHECK_CUDA(h, cudaMemcpyAsync(pairs_out, g->fl_pairs.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
+      H_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return RPGO_OK;
+  }
+  /* sharded rows: every rank flagged the pairs of its own row chunks; the list handed out is the union, rank by rank
+   * (collective: every rank calls this with the same arguments) */
+  const int W = h->cfg.world;
+  std::vector<long long> counts((size_t)2 * W, 0);
+  counts[h->cfg.rank] = (long long)c;
+  counts[W + h->cfg.rank] = (long long)mine;
+  if (comm_allreduce_i64_host(h->comm, counts.data(), counts.size(), true, h->stream) != 0) {
+    h->err = std::string("near_threshold exchange failed: ") + comm_error(h->comm);
+    return RPGO_ERR_CUDA;
+  }
+  int64_t total = 0, written = 0;
+  for (int r = 0; r < W; ++r) total += counts[r];
+  *n_out = total;
+  std::vector<int32_t> buf;
+  for (int r = 0; r < W; ++r) {
+    const int64_t m = counts[W + r];
+    if (m == 0) continue;
+    buf.assign((size_t)m * 2, 0);
+    if (r == h->cfg.rank) {
+      H_CHECK_CUDA(h, cudaMemcpyAsync(buf.data(), g->fl_pairs.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
+      H_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    if (comm_bcast_host(h->comm, buf.data(), (size_t)m * 8, r, h->stream) != 0) {
+      h->err = std::string("near_threshold exchange failed: ") + comm_error(h->comm);
+      return RPGO_ERR_CUDA;
+    }
+    const int64_t take = std::min<int64_t>(m, cap - written);
+    if (pairs_out && take > 0) memcpy(pairs_out + written * 2, buf.data(), (size_t)take * 8);
+    written += std::max<int64_t>(take, 0);
   }
   return RPGO_OK;
 }
 
 int rpgo_pair_distances(rpgo_handle* h, int32_t gi, double* dist_out) {
   if (!h || !dist_out) return RPGO_ERR_INVALID;
+  DeviceGuard dg(h->device);
   if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
   Group* g = h->groups[gi];
   const int64_t n = g->n;
@@ -1210,6 +1480,7 @@ int rpgo_pair_distances(rpgo_handle* h, int32_t gi, double* dist_out) {
 
 int rpgo_group_recompute(rpgo_handle* h, int32_t gi, int64_t j_begin) {
   if (!h) return RPGO_ERR_INVALID;
+  DeviceGuard dg(h->device);
   if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
   Group* g = h->groups[gi];
   if (j_begin < 0 || j_begin > g->n) return RPGO_ERR_INVALID;
@@ -1222,6 +1493,7 @@ int rpgo_group_recompute(rpgo_handle* h, int32_t gi, int64_t j_begin) {
 
 int rpgo_group_pairwise(rpgo_handle* h, int32_t gi, int64_t j_begin) {
   if (!h) return RPGO_ERR_INVALID;
+  DeviceGuard dg(h->device);
   if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
   Group* g = h->groups[gi];
   if (j_begin < 0 || j_begin > g->n) return RPGO_ERR_INVALID;
@@ -1231,8 +1503,23 @@ int rpgo_group_pairwise(rpgo_handle* h, int32_t gi, int64_t j_begin) {
 
 int rpgo_group_finalize(rpgo_handle* h, int32_t gi) {
   if (!h) return RPGO_ERR_INVALID;
+  DeviceGuard dg(h->device);
   if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
   return finalize_group(h, h->groups[gi], 0);
+}
+
+int rpgo_debug_pass(rpgo_handle* h, int32_t gi, int32_t which) {
+  if (!h) return RPGO_ERR_INVALID;
+  DeviceGuard dg(h->device);
+  if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
+  Group* g = h->groups[gi];
+  if (!g->bits.p || g->n < 1) return RPGO_ERR_INVALID;
+  if (which == 0) launch_mirror(g->bits.as<uint32_t>(), g->stride32, (int)g->n, 0, h->stream);
+  else if (which == 1) launch_degree(g->bits.as<uint32_t>(), g->stride32, (int)g->n, g->deg.as<int32_t>(), h->stream);
+  else return RPGO_ERR_INVALID;
+  h->launches += 1;
+  H_CHECK_CUDA(h, cudaGetLastError());
+  return RPGO_OK;
 }
 
 int rpgo_group_chunking(rpgo_handle* h, int32_t gi, int64_t* chunk_rows, int64_t* padded_rows) {
@@ -1247,6 +1534,7 @@ int rpgo_group_chunking(rpgo_handle* h, int32_t gi, int64_t* chunk_rows, int64_t
 int rpgo_debug_load_group(rpgo_handle* h, uint8_t id1, uint8_t id2, int64_t n, const uint64_t* rows,
                           int64_t stride_words, int32_t* group_out) {
   if (!h || n < 0 || (n > 0 && !rows) || stride_words < (n + 63) / 64) return RPGO_ERR_INVALID;
+  DeviceGuard dg(h->device);
   if (!h->loop_check) return RPGO_ERR_INVALID;
   const std::pair<uint8_t, uint8_t> id(std::min(id1, id2), std::max(id1, id2));
   int32_t gi;
@@ -1286,6 +1574,7 @@ int rpgo_debug_load_group(rpgo_handle* h, uint8_t id1, uint8_t id2, int64_t n, c
 int rpgo_frame_align_measurements(rpgo_handle* h, int32_t gi, uint8_t r0, int64_t m, const int32_t* closure_idx,
                                   double* T_out) {
   if (!h || m < 0 || (m > 0 && (!closure_idx || !T_out))) return RPGO_ERR_INVALID;
+  DeviceGuard dg(h->device);
   if (gi < 0 || gi >= (int32_t)h->groups.size()) return RPGO_ERR_NOT_FOUND;
   Group* g = h->groups[gi];
   if (g->landmark) return RPGO_ERR_INVALID;
@@ -1314,6 +1603,7 @@ int rpgo_frame_align_measurements(rpgo_handle* h, int32_t gi, uint8_t r0, int64_
 int rpgo_robot_odom_values(rpgo_handle* h, uint8_t prefix, const double* transform, int64_t cap, uint64_t* keys_out,
                            double* poses_out, int64_t* n_out) {
   if (!h || !n_out) return RPGO_ERR_INVALID;
+  DeviceGuard dg(h->device);
   std::vector<std::pair<uint64_t, int32_t>> ent;
   for (auto& kv : h->key2idx)
     if (key_chr(kv.first) == prefix) ent.push_back({kv.first, kv.second});
@@ -1358,7 +1648,10 @@ int rpgo_fp64_peak(int32_t device, double* tflops_out) {
   if (!tflops_out) return RPGO_ERR_INVALID;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return RPGO_ERR_CUDA;
-  if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return RPGO_ERR_CUDA;
+  if (device >= ndev) return RPGO_ERR_INVALID;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  DeviceGuard dg(device >= 0 ? device : cur);
   cudaStream_t st;
   if (cudaStreamCreate(&st) != cudaSuccess) return RPGO_ERR_CUDA;
   *tflops_out = fp64_peak_tflops(st);

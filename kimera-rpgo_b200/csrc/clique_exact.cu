@@ -361,11 +361,8 @@ static int clique_exact_warp(const uint32_t* bits, int64_t stride32, int n, int 
    * root without tasks (for those task_pre[i-1] == task_pre[i]) */
   EXCHECK(cudaMemcpyAsync(lowdeg, pre.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
   const size_t smem = (size_t)n * 32 * sizeof(uint32_t);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(exact_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 32 * 4);
-    attr = true;
-  }
+  static PerDeviceOnce attr;
+  if (attr.first()) cudaFuncSetAttribute(exact_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 32 * 4);
   int per_sm = (int)((200 * 1024) / (smem > 0 ? smem : 1));
   per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
   int grid = 148 * per_sm;
@@ -397,10 +394,10 @@ static int clique_exact_warp(const uint32_t* bits, int64_t stride32, int n, int 
   int xrc = 0, owner = 0;
   if (sharded) {
     long long key = (long long)hinc;
-    xrc = cs.exchange(cs.user, RPGO_XCHG_MAX_I64, &key, 1, 0);
+    xrc = cs.xchg(RPGO_XCHG_MAX_I64, &key, 1, 0);
     hinc = (unsigned long long)key;
     long long who = (mine == hinc) ? rank : -1; /* the incumbent's task ran on exactly one rank */
-    if (xrc == 0) xrc = cs.exchange(cs.user, RPGO_XCHG_MAX_I64, &who, 1, 0);
+    if (xrc == 0) xrc = cs.xchg(RPGO_XCHG_MAX_I64, &who, 1, 0);
     owner = (int)who;
   }
   const int size = (int)(hinc >> 42);
@@ -418,7 +415,7 @@ static int clique_exact_warp(const uint32_t* bits, int64_t stride32, int n, int 
         for (int l = 0; l < size; ++l) ids_out_host[l] = p[size - 1 - l]; /* ascending ids, as the reference returns them */
       }
     }
-    if (sharded && rc >= 0 && cs.exchange(cs.user, RPGO_XCHG_BCAST_I32, ids_out_host, size, owner) != 0) rc = -3;
+    if (sharded && rc >= 0 && cs.xchg(RPGO_XCHG_BCAST_I32, ids_out_host, size, owner) != 0) rc = -3;
   }
   cudaFree(lowdeg);
   cudaFree(stacks);
@@ -433,7 +430,7 @@ static int clique_exact_warp(const uint32_t* bits, int64_t stride32, int n, int 
 int clique_exact(const uint32_t* bits, int64_t stride32, int n, const int32_t* deg, CliqueScratch s, int32_t* ids_out_host,
                  int64_t* launches, cudaStream_t st, CliqueShard cs) {
   (void)s;
-  const bool sharded = cs.world > 1 && cs.exchange != nullptr;
+  const bool sharded = cs.active();
   const int world = sharded ? cs.world : 1, rank = sharded ? cs.rank : 0;
   if (n <= 0) return 0;
   const int W = (n + 31) / 32;
@@ -474,7 +471,7 @@ int clique_exact(const uint32_t* bits, int64_t stride32, int n, const int32_t* d
   if (sharded) {
     /* incumbent all-reduce: larger size, then larger root — the reference's preference between roots */
     long long key = (long long)hinc;
-    xrc = cs.exchange(cs.user, RPGO_XCHG_MAX_I64, &key, 1, 0);
+    xrc = cs.xchg(RPGO_XCHG_MAX_I64, &key, 1, 0);
     hinc = (unsigned long long)key;
   }
   const int size = (int)(hinc >> 32), root = (int)(hinc & 0xffffffffu);
@@ -488,7 +485,7 @@ int clique_exact(const uint32_t* bits, int64_t stride32, int n, const int32_t* d
       /* the reference returns the clique in ascending id order (ids pushed while unwinding) */
       for (int l = 0; l < size; ++l) ids_out_host[l] = p[size - 1 - l];
     }
-    if (sharded && cs.exchange(cs.user, RPGO_XCHG_BCAST_I32, ids_out_host, size, owner) != 0) rc = -3;
+    if (sharded && cs.xchg(RPGO_XCHG_BCAST_I32, ids_out_host, size, owner) != 0) rc = -3;
   }
   cudaFree(stacks);
   cudaFree(paths);

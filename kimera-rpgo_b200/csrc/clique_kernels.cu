@@ -507,17 +507,16 @@ __global__ void heu_select_kernel(int n, int K, const int32_t* __restrict__ elim
 int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_t* deg, int first, int maxclq0,
                      CliqueScratch s, int32_t* ids_out_host, int32_t* true_out_host, int64_t* launches,
                      cudaStream_t st, CliqueShard cs) {
-  const bool sharded = cs.world > 1 && cs.exchange != nullptr;
+  const bool sharded = cs.active();
   const int world = sharded ? cs.world : 1, rank = sharded ? cs.rank : 0;
   if (n <= 0) return -1;
   const int W = (n + 31) / 32;
   const size_t smem = (size_t)W * sizeof(uint32_t);
   if (smem > 200 * 1024) return -2; /* n > ~1.6M closures in one group: not supported by this kernel */
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.first()) {
     cudaFuncSetAttribute(heu_round_kernel<HEU_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(heu_round_kernel<HEU_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
   }
   static const char* wide_env = getenv("RPGO_CLIQUE_WIDE"); /* A/B knob: 0 / 1 forces the block size */
   const bool wide = wide_env ? (wide_env[0] == '1') : (n > HEU_WIDE_N);
@@ -549,11 +548,10 @@ int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_
   int start = first < 0 ? 0 : first;
   if (persistent) {
     /* single rank: all rounds in one cooperative launch */
-    static bool attr2 = false;
-    if (!attr2) {
+    static PerDeviceOnce attr2;
+    if (attr2.first()) {
       cudaFuncSetAttribute(heu_persistent_kernel<HEU_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       cudaFuncSetAttribute(heu_persistent_kernel<HEU_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr2 = true;
     }
     const void* pk = wide ? (const void*)heu_persistent_kernel<HEU_THREADS_WIDE> : (const void*)heu_persistent_kernel<HEU_THREADS>;
     int dev = 0, sms = 0, bps = 0;
@@ -622,7 +620,7 @@ int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_
       /* incumbent exchange: the lowest-index improving candidate over all ranks wins the round */
       const unsigned long long mine = h_ctl;
       long long key = (h_ctl == none) ? LLONG_MAX : (long long)h_ctl;
-      if (cs.exchange(cs.user, RPGO_XCHG_MIN_I64, &key, 1, 0) != 0) return -3;
+      if (cs.xchg(RPGO_XCHG_MIN_I64, &key, 1, 0) != 0) return -3;
       h_ctl = (key == LLONG_MAX) ? none : (unsigned long long)key;
       local_winner = (h_ctl == mine);
     }

@@ -4,10 +4,25 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "rpgo_math.cuh"
 #include "../../include/rpgo_b200.h"
 
 namespace rpgo {
+
+/* cudaFuncSetAttribute is per device: remember which devices have opted a kernel into its dynamic shared memory */
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  bool first() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ULL << (dev & 63);
+    if (mask.load(std::memory_order_relaxed) & bit) return false;
+    mask.fetch_or(bit);
+    return true; /* two racing threads both set the attribute: idempotent */
+  }
+};
 
 /* one odometry step: entries[out_idx] = entries[prev_idx] (or the running value) . T(delta) */
 struct FoldChain {
@@ -61,8 +76,10 @@ void launch_pairwise_direct(int dim, int mode, GroupView g, const double* traj, 
                             Flagged fl, double* dist_out, cudaStream_t st);
 int tiled_record_doubles(int dim);
 void launch_gather_records(int dim, GroupView g, const double* traj, int k0, double* aos, double* soa, cudaStream_t st);
+/* variant: 0 = default (phase-shifted warp groups, straight-line pair function); the two cross-check forms
+ * RPGO_KERNEL_TILED_ONE_GROUP / RPGO_KERNEL_TILED_V1 select 1 / 2 */
 void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, const double* soa, int j_begin, Shard sh,
-                           Thresholds th, Flagged fl, cudaStream_t st);
+                           Thresholds th, Flagged fl, int variant, cudaStream_t st);
 /* N3: landmark re-observation matrix (one thread per pair of observations of the same landmark) */
 void launch_landmark_direct(int dim, int mode, GroupView g, const double* traj, int j_begin, Thresholds th, Flagged fl,
                             double* dist_out, cudaStream_t st);
@@ -86,12 +103,18 @@ struct CliqueScratch {
   uint32_t* rwork;          /* per-block working sets: grid x stride32 */
   int64_t rwork_blocks;
 };
-/* candidate partition of the clique searches over ranks; exchange is the host-provided collective
- * (rpgo_set_exchange): op RPGO_XCHG_*, in place on buf */
+/* candidate partition of the clique searches over ranks; the incumbent is combined over the handle's NCCL communicator
+ * (rpgo_comm_init) or, when the caller brings its own collective, the host function of rpgo_set_exchange */
+struct Comm;
 struct CliqueShard {
   int rank = 0, world = 1;
   int (*exchange)(void* user, int32_t op, void* buf, int64_t count, int32_t root) = nullptr;
   void* user = nullptr;
+  Comm* comm = nullptr;          /* NCCL communicator of the handle (rpgo_comm_init); preferred over `exchange` */
+  cudaStream_t comm_stream = nullptr;
+  bool active() const { return world > 1 && (comm != nullptr || exchange != nullptr); }
+  /* in-place collective on a HOST buffer, same on every rank: RPGO_XCHG_* */
+  int xchg(int32_t op, void* buf, int64_t count, int32_t root) const;
 };
 int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_t* deg, int first, int maxclq0,
                      CliqueScratch s, int32_t* ids_out_host, int32_t* true_out_host, int64_t* launches,

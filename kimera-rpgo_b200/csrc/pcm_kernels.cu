@@ -580,8 +580,6 @@ __global__ void __launch_bounds__(128, MINB) pairwise_direct_kernel(GroupView g,
   }
 }
 
-int g_direct_minb = 2; /* experiment knob: min blocks/SM of the direct kernel (register cap) */
-
 void launch_pairwise_direct(int dim, int mode, GroupView g, const double* traj, int j_begin, Shard sh, Thresholds th,
                             Flagged fl, double* dist_out, cudaStream_t st) {
   if (g.n < 2 || j_begin >= g.n) return;
@@ -589,14 +587,6 @@ void launch_pairwise_direct(int dim, int mode, GroupView g, const double* traj, 
   const int w_end = (g.n + 31) / 32;
   const int warps = 4;
   dim3 grid(w_end - w_begin, (g.n + warps - 1) / warps);
-  if (dim == 3 && mode == MODE_PCM && g_direct_minb == 3) {
-    pairwise_direct_kernel<3, MODE_PCM, 3><<<grid, warps * 32, 0, st>>>(g, traj, j_begin, w_begin, sh, th, fl, dist_out);
-    return;
-  }
-  if (dim == 3 && mode == MODE_PCM && g_direct_minb == 4) {
-    pairwise_direct_kernel<3, MODE_PCM, 4><<<grid, warps * 32, 0, st>>>(g, traj, j_begin, w_begin, sh, th, fl, dist_out);
-    return;
-  }
 #define CALL(D, M) pairwise_direct_kernel<D, M, 2><<<grid, warps * 32, 0, st>>>(g, traj, j_begin, w_begin, sh, th, fl, dist_out)
   RPGO_DISPATCH(dim, mode, CALL);
 #undef CALL
@@ -825,4 +815,3 @@ double fp64_peak_tflops(cudaStream_t st) {
 }
 
 }  // namespace rpgo
-int g_direct_minb_set(int v) { rpgo::g_direct_minb = v; return v; }

@@ -19,6 +19,7 @@
  *     one-group form kept for A/B measurements.
  * FP64 CUDA-core bound by design (6x6 / 3x3 fp64 with data-dependent branches: no tensor cores).
  */
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 
@@ -220,7 +221,7 @@ __device__ __forceinline__ void group_of(int w, int& grp, int& wi) {
 template <int D, int TILE_WARPS, int G, int SEG>
 __global__ void __launch_bounds__(TILE_WARPS * 32, 1)
     pairwise_grouped_kernel(GroupView g, const double* __restrict__ aos, const double* __restrict__ soa, int j_begin,
-                            int cb_begin, Shard sh, Thresholds th, Flagged fl, int stagger_ns) {
+                            int cb_begin, Shard sh, Thresholds th, Flagged fl) {
   constexpr int RN = Rec<D>::N;
   constexpr int WG = TILE_WARPS / G;
   static_assert(WG * G == TILE_WARPS, "groups must divide the block");
@@ -263,7 +264,6 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 1)
     tma_load_1d(Ig, aos + (size_t)first * RN, (uint32_t)(rows * RN * 8), &gb[0]);
   }
   mbar_wait(&bars[0], 0);
-  if (G > 1 && grp > 0 && stagger_ns > 0) __nanosleep((unsigned)(grp * stagger_ns));
 
   const int j = cb * 32 + lane;
   const double* Jl = Jt + lane;
@@ -375,11 +375,8 @@ static void launch_column(GroupView g, const double* aos, const double* soa, int
                           cudaStream_t st) {
   constexpr int TW = 12;
   const size_t smem = ((Rec<D>::N * 8 + 127) / 128) * 128 + (size_t)Rec<D>::E * TW * 32 * 8;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(pairwise_column_kernel<D, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = true;
-  }
+  static PerDeviceOnce once;
+  if (once.first()) cudaFuncSetAttribute(pairwise_column_kernel<D, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int slabs = (g.n + 31) / 32;
   dim3 grid((slabs + TW - 1) / TW, g.n - j_begin);
   pairwise_column_kernel<D, TW><<<grid, TW * 32, smem, st>>>(g, aos, soa, j_begin, sh, th, fl);
@@ -447,49 +444,47 @@ int fastmath_check(long long n, unsigned long long seed, unsigned long long* mis
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
-int g_tiled_variant = 6; /* 6 = 12 warps x 1 block/SM in 3 phase-shifted groups, straight-line pair function (default); 4 = same, one group; 2 = same with pair_check_v1; experiment knobs: 0 = 4 warps x 2 blocks, 1 = 10 x 1, 3 = 8 x 1 */
-
 template <int D, int TW, int MINB, int PAIRFN>
 static void launch_variant(GroupView g, const double* aos, const double* soa, int j_begin, int cb_begin, dim3 grid, Shard sh,
                            Thresholds th, Flagged fl, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce once;
+  if (once.first())
     cudaFuncSetAttribute(pairwise_tiled_kernel<D, TW, MINB, PAIRFN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)TiledSmem<D, TW>::BYTES);
-    attr = true;
-  }
   pairwise_tiled_kernel<D, TW, MINB, PAIRFN><<<grid, TW * 32, TiledSmem<D, TW>::BYTES, st>>>(g, aos, soa, j_begin, cb_begin, sh, th, fl);
 }
 
-int g_stagger_ns = -1;
 template <int D, int TW, int G, int SEG>
 static void launch_grouped(GroupView g, const double* aos, const double* soa, int j_begin, int cb_begin, int cb_end, Shard sh,
                            Thresholds th, Flagged fl, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce once;
+  if (once.first())
     cudaFuncSetAttribute(pairwise_grouped_kernel<D, TW, G, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)TiledSmem<D, TW>::BYTES);
-    attr = true;
-  }
-  if (g_stagger_ns < 0) {
-    const char* e = getenv("RPGO_STAGGER_NS");
-    g_stagger_ns = e ? atoi(e) : 0; /* measured: the groups drift apart on their own */
-  }
   dim3 grid((g.n + SEG - 1) / SEG, cb_end - cb_begin);
-  pairwise_grouped_kernel<D, TW, G, SEG><<<grid, TW * 32, TiledSmem<D, TW>::BYTES, st>>>(g, aos, soa, j_begin, cb_begin, sh, th, fl,
-                                                                                           g_stagger_ns);
+  pairwise_grouped_kernel<D, TW, G, SEG><<<grid, TW * 32, TiledSmem<D, TW>::BYTES, st>>>(g, aos, soa, j_begin, cb_begin, sh, th, fl);
 }
 
 void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, const double* soa, int j_begin, Shard sh,
-                           Thresholds th, Flagged fl, cudaStream_t st) {
+                           Thresholds th, Flagged fl, int variant, cudaStream_t st) {
   (void)mode; /* MODE_PCM only */
   if (g.n < 2 || j_begin >= g.n) return;
   const int cb_begin = j_begin / 32;
   const int cb_end = (g.n + 31) / 32;
   dim3 grid((g.n + TILE_SEG - 1) / TILE_SEG, cb_end - cb_begin);
+  if (variant != 0) {
+    /* cross-check forms for the parity tests: one warp group, straight-line (1) or plain branchy (2) pair function */
+    if (dim == 3) {
+      if (variant == 1) launch_variant<3, 12, 1, 2>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st);
+      else launch_variant<3, 12, 1, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st);
+    } else {
+      if (variant == 1) launch_variant<2, 12, 1, 2>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st);
+      else launch_variant<2, 12, 1, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st);
+    }
+    return;
+  }
   /* online case: a handful of new closures against a large group -> lanes over the older closures */
-  static const bool no_column = getenv("RPGO_NO_COLUMN_KERNEL") != nullptr;
-  if (g_tiled_variant == 6 && !no_column && g.n - j_begin <= 32 && j_begin >= 32) {
+  if (g.n - j_begin <= 32 && j_begin >= 32) {
     if (dim == 3) launch_column<3>(g, aos, soa, j_begin, sh, th, fl, st);
     else launch_column<2>(g, aos, soa, j_begin, sh, th, fl, st);
     return;
@@ -498,37 +493,13 @@ void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, co
    * launch fills the SMs and a block is 4 iterations long instead of 43 (latency of a single-closure update) */
   const long long items512 = (long long)((g.n + TILE_SEG - 1) / TILE_SEG) * (cb_end - cb_begin);
   const bool small = items512 < 4LL * 148;
-  if (g_tiled_variant == 6 && small) {
+  if (small) {
     if (dim == 3) launch_grouped<3, 12, 3, 48>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st);
     else launch_grouped<2, 12, 3, 48>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st);
     return;
   }
-  if (dim == 3 && g_tiled_variant >= 5) {
-    switch (g_tiled_variant) {
-      case 5: launch_grouped<3, 12, 2, 512>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); break;
-      case 6: launch_grouped<3, 12, 3, 504>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); break; /* 42 x 12 rows: no ragged last iteration */
-      case 7: launch_grouped<3, 12, 3, 512>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); break;
-      case 10: launch_grouped<3, 12, 6, 512>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); break;
-      case 11: launch_grouped<3, 12, 12, 512>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); break;
-      case 8: launch_grouped<3, 12, 4, 512>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); break;
-      default: launch_grouped<3, 12, 1, 512>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); break;
-    }
-    return;
-  }
-  if (dim == 3) {
-    switch (g_tiled_variant) {
-      case 1: launch_variant<3, 10, 1, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st); break;
-      case 3: launch_variant<3, 8, 1, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st); break;
-      case 0: launch_variant<3, 4, 2, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st); break;
-      case 2: launch_variant<3, 12, 1, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st); break;
-      default: launch_variant<3, 12, 1, 2>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st); break;
-    }
-  } else {
-    if (g_tiled_variant >= 5) launch_grouped<2, 12, 3, 512>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st);
-    else if (g_tiled_variant == 2) launch_variant<2, 12, 1, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st);
-    else launch_variant<2, 12, 1, 2>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st);
-  }
+  if (dim == 3) launch_grouped<3, 12, 3, 504>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); /* 42 x 12 rows: no ragged last iteration */
+  else launch_grouped<2, 12, 3, 512>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st);
 }
 
 }  // namespace rpgo
-int g_tiled_variant_set(int v) { rpgo::g_tiled_variant = v; return v; }

@@ -1,23 +1,31 @@
-"""Multi-GPU plumbing for the one exchange step the path has: the all-gather of adjacency row chunks.
+"""Multi-GPU plumbing around the C ABI.
 
-One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch).  Every rank holds the replicated
-trajectory and closure tables and computes the upper-triangle pair checks of its row chunks
-{rank, 2*world-1-rank} (pairing a long and a short chunk balances the triangle).  The chunks are then
-all-gathered in place and every rank rebuilds the lower triangle and the degrees locally
-(rpgo_group_finalize).  The same function runs on CPU tensors with the gloo backend for the tests."""
+The data plane itself is C++/NCCL inside the library (csrc/comm.cu: rpgo_comm_init, the all-gather of adjacency row
+chunks inside rpgo_lc_append, the incumbent all-reduce of the clique searches).  What lives here is
+  * `comm_id_via_torch` / `attach_comm`: hand rank 0's NCCL unique id to the other ranks over an existing
+    torch.distributed process group (one process per GPU) and build the handle's communicator;
+  * `exchange_row_chunks`: the same exchange protocol written with torch.distributed collectives.  It mirrors
+    comm.cu::comm_allgather_row_chunks step by step (in-place all-gather of the low chunks, one broadcast per rank for
+    the mirrored high chunks) and runs on CPU tensors with the gloo backend, which is how the chunk layout is tested
+    without GPUs;
+  * `make_exchange`: a host collective for rpgo_set_exchange (bring-your-own transport; gloo in the tests).
+Every rank holds the replicated trajectory and closure tables and computes the upper-triangle pair checks of its row
+chunks {rank, 2*world-1-rank} (pairing a long and a short chunk balances the triangle)."""
 import torch
 import torch.distributed as dist
 
 
-class _DevMem:
-    """Zero-copy view of library-owned device memory for torch (via __cuda_array_interface__)."""
+def comm_id_via_torch(unique_id_fn, group=None):
+    """rank 0 calls unique_id_fn() (PcmGpu.comm_unique_id); returns the same 128 bytes on every rank."""
+    box = [unique_id_fn() if dist.get_rank(group) == 0 else None]
+    dist.broadcast_object_list(box, src=0 if group is None else dist.get_global_rank(group, 0), group=group)
+    return box[0]
 
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
-
-def tensor_from_device_ptr(ptr, nbytes, device):
-    return torch.as_tensor(_DevMem(ptr, nbytes), device=device)
+def attach_comm(pcm, group=None):
+    """Collective over the process group: give `pcm` (created with rank/world of this group) its NCCL communicator."""
+    pcm.comm_init(comm_id_via_torch(type(pcm).comm_unique_id, group))
+    return pcm
 
 
 def owned_chunks(rank, world):
@@ -26,29 +34,18 @@ def owned_chunks(rank, world):
 
 def exchange_row_chunks(t, rank, world, chunk_rows, group=None):
     """t: (2*world*chunk_rows, row_words) integer tensor whose rows in this rank's two chunks are valid.
-    After the call every rank holds all rows.  Two all-gathers of equal-size chunks."""
+    After the call every rank holds all rows.  Same sequence as comm.cu: one in-place all-gather of chunks 0..world-1
+    (rank r's chunk sits at slot r), then for every rank q a broadcast of chunk 2*world-1-q from q."""
     if world == 1:
         return t
     lo = [t[q * chunk_rows:(q + 1) * chunk_rows] for q in range(world)]
-    hi = [t[(2 * world - 1 - q) * chunk_rows:(2 * world - q) * chunk_rows] for q in range(world)]
     mine_lo = lo[rank].clone()
-    mine_hi = hi[rank].clone()
     dist.all_gather(lo, mine_lo, group=group)
-    dist.all_gather(hi, mine_hi, group=group)
+    for q in range(world):
+        c = 2 * world - 1 - q
+        src = q if group is None else dist.get_global_rank(group, q)
+        dist.broadcast(t[c * chunk_rows:(c + 1) * chunk_rows], src=src, group=group)
     return t
-
-
-def allgather_adjacency(pcm, g, device, group=None):
-    """All-gather group g's adjacency rows across ranks on the handle's stream, then finalize."""
-    world = pcm.cfg.world
-    if world > 1:
-        ptr, sw64, n = pcm.adj_bits_device(g)
-        chunk_rows, padded = pcm.group_chunking(g)
-        t = tensor_from_device_ptr(ptr, padded * sw64 * 8, device).view(torch.int64).view(padded, sw64)
-        st = torch.cuda.ExternalStream(pcm.stream_ptr(), device=device)
-        with torch.cuda.stream(st):
-            exchange_row_chunks(t, pcm.cfg.rank, world, chunk_rows, group=group)
-    pcm.finalize(g)
 
 
 def make_exchange(device=None, group=None):

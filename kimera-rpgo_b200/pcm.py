@@ -38,7 +38,7 @@ class PcmGpu:
 
     def __init__(self, d=3, mode=MODE_PCM, odom_threshold=10.0, lc_threshold=5.0, odom_trans=0.05, odom_rot=0.005,
                  dist_trans=0.01, dist_rot=0.001, incremental=False, device=-1, traj_mode=TRAJ_FOLD,
-                 kernel=KERNEL_AUTO, rank=0, world=1, special_symbols=(), scan_chunk=64):
+                 kernel=KERNEL_AUTO, rank=0, world=1, special_symbols=(), scan_chunk=64, comm_id=None):
         self.lib = _capi.load()
         cfg = _capi.RpgoCfg()
         self.lib.rpgo_default_cfg(C.byref(cfg))
@@ -55,16 +55,10 @@ class PcmGpu:
         if rc != 0:
             raise RpgoError("rpgo_create failed with status %d (no usable CUDA device? there is no CPU fallback)" % rc)
         self.d, self.mode = d, mode
-        self.auto_exchange = True
         self._exchange_cb = None
-        if world > 1:
-            # sharded clique searches: register the incumbent exchange when a process group is up
-            import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized() and dist.get_world_size() == world:
-                import torch
-                from . import parallel
-                dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else None
-                self.set_exchange(parallel.make_exchange(dev))
+        self.has_comm = False
+        if world > 1 and comm_id is not None:
+            self.comm_init(comm_id)
         self.ps = 12 if d == 3 else 4
         self.n = 6 if d == 3 else 3
         self.incremental = bool(incremental)
@@ -72,6 +66,14 @@ class PcmGpu:
         self.odom_check = not (odom_threshold < 0 or odom_rot < 0 or odom_trans < 0)
         self.loop_check = not (lc_threshold < 0 or dist_rot < 0 or dist_trans < 0)
         self.special_symbols = set(ord(c) if isinstance(c, str) else int(c) for c in special_symbols)
+        self._clear_host_state()
+
+    def reset(self):
+        """A fresh Pcm object on the same handle (rpgo_reset keeps stream, arena, pinned staging, communicator)."""
+        self._check(self.lib.rpgo_reset(self.h), "rpgo_reset")
+        self._clear_host_state()
+
+    def _clear_host_state(self):
         self.values = {}
         self.nfg_odom, self.nfg_special = [], []
         self.special_is_prior = {}     # factor id -> prior key (for removePriorFactorsWithPrefix)
@@ -115,6 +117,23 @@ class PcmGpu:
             f.write("%d %d %d %d\n" % (self.total_lc, self.total_good_lc, int(spin_s * 1e3), int(clique_s * 1e3)))
         with open(os.path.join(folder, "rpgo_status.csv"), "a") as f:  # RobustSolver::update
             f.write("%d,%d,%d,%d\n" % (len(self.output), int(spin_s * 1e6), self.total_lc, self.total_good_lc))
+
+    # ---- multi-GPU data plane (rpgo_comm_*: NCCL behind the C ABI) ------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """128 opaque bytes from rank 0 (ncclGetUniqueId); hand them to every rank, then call comm_init everywhere."""
+        buf = C.create_string_buffer(_capi.COMM_ID_BYTES)
+        rc = _capi.load().rpgo_comm_unique_id(buf)
+        if rc != 0:
+            raise RpgoError("rpgo_comm_unique_id failed (%d): NCCL not available?" % rc)
+        return buf.raw
+
+    def comm_init(self, comm_id):
+        """Collective: every rank of the world calls this with rank 0's id."""
+        assert len(comm_id) == _capi.COMM_ID_BYTES
+        buf = C.create_string_buffer(bytes(comm_id), _capi.COMM_ID_BYTES)
+        self._check(self.lib.rpgo_comm_init(self.h, C.cast(buf, C.c_void_p), self.cfg.rank, self.cfg.world), "rpgo_comm_init")
+        self.has_comm = True
 
     def set_exchange(self, cb):
         """Register (or clear, cb=None) the collective the sharded clique searches call; see rpgo_set_exchange."""
@@ -274,13 +293,9 @@ class PcmGpu:
         self.total_lc += int(ok.sum())
         self.last_h2d_bytes = pose.nbytes + cov.nbytes + 9 * n
         self.last_d2h_bytes = n
-        if self.cfg.world > 1 and self.loop_check and self.auto_exchange:
-            # multi-GPU: this rank computed only its row chunks; all-gather them and rebuild the mirror
-            from . import parallel
-            import torch
-            dev = torch.device("cuda", torch.cuda.current_device())
-            for g in num_new:
-                parallel.allgather_adjacency(self, g, dev)
+        self.last_group, self.last_index = grp, idx   # per input closure: group ordinal / position in it (-1: rejected)
+        # multi-GPU: with a communicator (comm_init) the library has all-gathered the row chunks and rebuilt mirror +
+        # degrees on every rank before rpgo_lc_append returned
         return num_new, acc
 
     # ---- landmarks (Pcm.h:207-220, :437-455, :775-844) -----------------------------------------
@@ -610,6 +625,14 @@ class PcmGpu:
 
     def finalize(self, g):
         self._check(self.lib.rpgo_group_finalize(self.h, g), "rpgo_group_finalize")
+
+    def debug_pass(self, g, which):
+        """one bitset pass alone (0 = mirror, 1 = degrees): bandwidth measurements"""
+        self._check(self.lib.rpgo_debug_pass(self.h, g, which), "rpgo_debug_pass")
+
+    def allgather(self, g):
+        """all-gather of group g's row chunks over the handle's communicator + mirror + degrees"""
+        self._check(self.lib.rpgo_group_allgather(self.h, g), "rpgo_group_allgather")
 
     def adj_bits_device(self, g):
         ptr, sw, n = C.c_void_p(), C.c_int64(), C.c_int64()

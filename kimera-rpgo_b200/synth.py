@@ -215,4 +215,5 @@ def as_arrays(gph):
     out["l_pose"] = np.ascontiguousarray(np.stack([f[3] for f in lc])).reshape(len(lc), ps)
     out["l_cov"] = np.ascontiguousarray(np.stack([np.asarray(f[4]).reshape(nn) for f in lc]))
     out["v_keys"] = np.array([k for k, _ in gph["values"]], dtype=np.uint64)
+    out["v_pose"] = np.ascontiguousarray(np.stack([p for _, p in gph["values"]])).reshape(len(gph["values"]), ps)
     return out

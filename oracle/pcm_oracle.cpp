@@ -752,6 +752,35 @@ int orc_update(void* h, int nf, const int* types, const uint64_t* k1, const uint
   }
   return o->remove_outliers(fs, nvs) ? 1 : 0;
 }
+/* Pcm::areLoopsConsistent (Pcm.h:670-718) for explicit pairs of a closure table, against the trajectories this oracle
+ * has folded so far: pair t = (closure pi[t] as a_lc_b — the OLDER one —, closure pj[t] as c_lc_d).  Lets the parity tests
+ * check sampled pairs of matrices far too large to build on one core.  ok_out[t] = decision, dist_out[t] = the distance
+ * it was taken on, band_out[t] = 1 when |dist - threshold| < band (the near-threshold flag, PCM mode). */
+void orc_check_pairs(void* h, int n, const uint64_t* k1, const uint64_t* k2, const double* poses, const double* covs,
+                     long long m, const int* pi, const int* pj, unsigned char* ok_out, double* dist_out, unsigned char* band_out) {
+  Oracle* o = (Oracle*)h;
+  const int ps = o->d == 3 ? 12 : 4, nn = o_n(o->d) * o_n(o->d);
+  auto make = [&](int i) {
+    Factor f;
+    memset(&f, 0, sizeof(Factor));
+    f.type = 0;
+    f.k1 = k1[i];
+    f.k2 = k2[i];
+    memcpy(f.pose, poses + (size_t)i * ps, sizeof(double) * ps);
+    memcpy(f.cov, covs + (size_t)i * nn, sizeof(double) * nn);
+    f.id = i;
+    return f;
+  };
+  (void)n;
+  for (long long t = 0; t < m; ++t) {
+    const Factor a = make(pi[t]), c = make(pj[t]);
+    double dist = 0.0;
+    const bool ok = o->are_loops_consistent(a, c, &dist);
+    if (ok_out) ok_out[t] = ok ? 1 : 0;
+    if (dist_out) dist_out[t] = dist;
+    if (band_out) band_out[t] = (o->mode == MODE_PCM && fabs(dist - o->lc_threshold) < o->band) ? 1 : 0;
+  }
+}
 long long orc_num_lc(void* h) { return (long long)((Oracle*)h)->total_lc; }
 long long orc_num_inliers(void* h) { return (long long)((Oracle*)h)->total_good_lc; }
 long long orc_num_odom(void* h) { return (long long)((Oracle*)h)->nfg_odom.size(); }

@@ -41,6 +41,8 @@ def lib():
         L.orc_landmark_adj.restype = C.c_int
         L.orc_landmark_adj.argtypes = [C.c_void_p, C.c_int, c_u8p, c_dp]
         L.orc_landmark_ids.argtypes = [C.c_void_p, C.c_int, c_llp, c_llp]
+        L.orc_check_pairs.restype = None
+        L.orc_check_pairs.argtypes = [C.c_void_p, C.c_int, c_u64p, c_u64p, c_dp, c_dp, C.c_longlong, c_ip, c_ip, c_u8p, c_dp, c_u8p]
         L.orc_update.restype = C.c_int
         L.orc_update.argtypes = [C.c_void_p, C.c_int, c_ip, c_u64p, c_u64p, c_dp, c_dp, C.c_int, c_u64p, c_dp]
         for n in ["orc_num_lc", "orc_num_inliers", "orc_num_odom", "orc_num_special", "orc_num_values",
@@ -301,6 +303,41 @@ class OraclePcm:
             vk = np.zeros(1, dtype=np.uint64)
         return bool(lib().orc_update(self.h, nf, types.ctypes.data_as(c_ip), k1.ctypes.data_as(c_u64p),
                                      k2.ctypes.data_as(c_u64p), dp(poses), dp(covs), nv, vk.ctypes.data_as(c_u64p), dp(vp)))
+
+    def update_arrays(self, k1, k2, poses, covs, vkeys=None, vposes=None):
+        """update() for BetweenFactors given as arrays (what synth.as_arrays produces): no per-factor Python work."""
+        nf = len(k1)
+        ps, nn = psize(self.d), ndim(self.d) ** 2
+        types = np.zeros(max(nf, 1), dtype=np.int32)
+        k1 = np.ascontiguousarray(k1, dtype=np.uint64) if nf else np.zeros(1, dtype=np.uint64)
+        k2 = np.ascontiguousarray(k2, dtype=np.uint64) if nf else np.zeros(1, dtype=np.uint64)
+        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(max(nf, 1), ps) if nf else np.zeros((1, ps))
+        covs = np.ascontiguousarray(covs, dtype=np.float64).reshape(max(nf, 1), nn) if nf else np.zeros((1, nn))
+        nv = 0 if vkeys is None else len(vkeys)
+        vk = np.ascontiguousarray(vkeys, dtype=np.uint64) if nv else np.zeros(1, dtype=np.uint64)
+        vp = np.ascontiguousarray(vposes, dtype=np.float64).reshape(nv, ps) if nv else np.zeros((1, ps))
+        return bool(lib().orc_update(self.h, nf, types.ctypes.data_as(c_ip), k1.ctypes.data_as(c_u64p),
+                                     k2.ctypes.data_as(c_u64p), dp(poses), dp(covs), nv, vk.ctypes.data_as(c_u64p), dp(vp)))
+
+    def check_pairs(self, k1, k2, poses, covs, pi, pj):
+        """areLoopsConsistent (Pcm.h:670-718) for the pairs (pi[t] older, pj[t] newer) of a closure table given as arrays
+        (keys, n x ps poses, n x N*N covariances), against the trajectories folded so far.
+        Returns (ok uint8[m], dist float64[m], in_band uint8[m])."""
+        n = len(k1)
+        k1 = np.ascontiguousarray(k1, dtype=np.uint64)
+        k2 = np.ascontiguousarray(k2, dtype=np.uint64)
+        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(n, psize(self.d))
+        covs = np.ascontiguousarray(covs, dtype=np.float64).reshape(n, ndim(self.d) ** 2)
+        pi = np.ascontiguousarray(pi, dtype=np.int32)
+        pj = np.ascontiguousarray(pj, dtype=np.int32)
+        m = len(pi)
+        ok = np.zeros(max(m, 1), dtype=np.uint8)
+        band = np.zeros(max(m, 1), dtype=np.uint8)
+        dist = np.zeros(max(m, 1))
+        lib().orc_check_pairs(self.h, n, k1.ctypes.data_as(c_u64p), k2.ctypes.data_as(c_u64p), dp(poses), dp(covs), m,
+                              pi.ctypes.data_as(c_ip), pj.ctypes.data_as(c_ip), ok.ctypes.data_as(c_u8p), dp(dist),
+                              band.ctypes.data_as(c_u8p))
+        return ok[:m], dist[:m], band[:m]
 
     def nfg_size(self):
         return lib().orc_output_size(self.h)
