@@ -236,6 +236,10 @@ int rpgo_group_pairwise(rpgo_handle* h, int32_t g, int64_t j_begin);
 /* multi-GPU: after the caller has all-gathered the upper-triangle row chunks, rebuild the lower
  * triangle and the degrees on this GPU */
 int rpgo_group_finalize(rpgo_handle* h, int32_t g);
+/* statistics of the last heuristic search of rpgo_find_inliers on this rank: adjacency-row ANDs (one n/8-byte row per
+ * greedy step plus the initial row of every evaluated candidate: the algorithmic bytes of SURVEY §8(d) are row_ands * n / 8),
+ * greedy chains started, and epochs (dependent passes over the candidates) */
+int rpgo_clique_stats(rpgo_handle* h, int64_t* row_ands, int64_t* chains, int32_t* epochs);
 /* one bitset pass alone, for bandwidth measurements: which = 0 mirror (lower triangle from the upper one), 1 degrees */
 int rpgo_debug_pass(rpgo_handle* h, int32_t g, int32_t which);
 /* row-chunk geometry of group g for the all-gather: rows are cut into 2*world chunks of chunk_rows rows */

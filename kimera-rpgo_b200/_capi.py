@@ -60,6 +60,7 @@ SYMBOLS = [
     ("rpgo_group_recompute", C.c_int, [C.c_void_p, C.c_int32, C.c_int64]),
     ("rpgo_group_pairwise", C.c_int, [C.c_void_p, C.c_int32, C.c_int64]),
     ("rpgo_group_finalize", C.c_int, [C.c_void_p, C.c_int32]),
+    ("rpgo_clique_stats", C.c_int, [C.c_void_p, c_i64p, c_i64p, c_i32p]),
     ("rpgo_debug_pass", C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     ("rpgo_group_chunking", C.c_int, [C.c_void_p, C.c_int32, c_i64p, c_i64p]),
     ("rpgo_launch_count", C.c_int64, [C.c_void_p]),

@@ -252,6 +252,7 @@ struct rpgo_handle {
   cudaEvent_t ev_stage = nullptr; /* marks the end of the last H2D copy out of the pinned staging buffer */
   std::string err;
   int64_t launches = 0;
+  CliqueStats last_clique;         /* statistics of the last rpgo_find_inliers heuristic search */
   rpgo_exchange_fn xchg = nullptr; /* incumbent exchange of the sharded clique searches */
   void* xchg_user = nullptr;
 
@@ -1147,7 +1148,7 @@ int rpgo_lc_remove_last(rpgo_handle* h, int32_t gi, uint64_t* key_from, uint64_t
 /* one clique search on an explicit scratch set / stream (shared by the single and the batched entry point) */
 static int run_clique(rpgo_handle* h, Group* g, int32_t clique_mode, int64_t n_new, int64_t prev_size, CliqueSet* cset,
                       cudaStream_t st, CliqueShard cs, int32_t* ids_out, int64_t* size_out, int32_t* true_clique_out,
-                      int64_t* launches, std::string* err) {
+                      int64_t* launches, std::string* err, CliqueStats* stats = nullptr) {
   const int n = (int)g->n;
   CliqueScratch s;
   s.degmask = cset->degmask.as<uint32_t>();
@@ -1160,13 +1161,13 @@ static int run_clique(rpgo_handle* h, Group* g, int32_t clique_mode, int64_t n_n
   int r;
   if (clique_mode == RPGO_CLIQUE_HEU) {
     r = clique_heuristic(g->bits.as<uint32_t>(), g->stride32, n, g->deg.as<int32_t>(), 0, -1, s, ids_out, true_clique_out,
-                         launches, st, cs);
+                         launches, st, cs, stats);
     if (r < -1) { *err = "clique_heuristic failed: " + std::to_string(r); return RPGO_ERR_CUDA; }
     *size_out = r;
   } else if (clique_mode == RPGO_CLIQUE_HEU_INCREMENTAL) {
     if (n_new < 0 || n_new > n || prev_size < 0) return RPGO_ERR_INVALID;
     r = clique_heuristic(g->bits.as<uint32_t>(), g->stride32, n, g->deg.as<int32_t>(), (int)(n - n_new), (int)prev_size, s,
-                         ids_out, true_clique_out, launches, st, cs);
+                         ids_out, true_clique_out, launches, st, cs, stats);
     if (r < -1) { *err = "clique_heuristic failed: " + std::to_string(r); return RPGO_ERR_CUDA; }
     *size_out = (r > prev_size) ? r : 0; /* GraphUtils.cpp:40-43 */
   } else if (clique_mode == RPGO_CLIQUE_EXACT) {
@@ -1186,8 +1187,8 @@ static cudaError_t ensure_clique_set(CliqueSet* c, int n, cudaStream_t st) {
   if ((e = c->picks.ensure((size_t)n * 4 + 64, 0, st)) != cudaSuccess) return e;
   if ((e = c->elim.ensure((size_t)n * 4 + 64, 0, st)) != cudaSuccess) return e;
   if ((e = c->result.ensure((size_t)n * 4 + 64, 0, st)) != cudaSuccess) return e;
-  if ((e = c->ctl.ensure(64, 0, st)) != cudaSuccess) return e;
-  return c->rwork.ensure((size_t)CLIQUE_BLOCKS * n * 4 + (size_t)W * 8 + 64, 0, st);
+  if ((e = c->ctl.ensure(clique_ctl_bytes(CLIQUE_BLOCKS), 0, st)) != cudaSuccess) return e;
+  return c->rwork.ensure((size_t)CLIQUE_BLOCKS * 2 * n * 4 + (size_t)W * 8 + 64, 0, st);
 }
 
 int rpgo_find_inliers(rpgo_handle* h, int32_t gi, int32_t clique_mode, int64_t n_new, int64_t prev_size,
@@ -1202,7 +1203,15 @@ int rpgo_find_inliers(rpgo_handle* h, int32_t gi, int32_t clique_mode, int64_t n
   H_CHECK_CUDA(h, ensure_clique_set(&h->cset, n, st));
   const CliqueShard cs = clique_shard(h, st);
   return run_clique(h, g, clique_mode, n_new, prev_size, &h->cset, st, cs, ids_out, size_out, true_clique_out, &h->launches,
-                    &h->err);
+                    &h->err, &h->last_clique);
+}
+
+int rpgo_clique_stats(rpgo_handle* h, int64_t* row_ands, int64_t* chains, int32_t* epochs) {
+  if (!h) return RPGO_ERR_INVALID;
+  if (row_ands) *row_ands = h->last_clique.row_ands;
+  if (chains) *chains = h->last_clique.chains;
+  if (epochs) *epochs = h->last_clique.epochs;
+  return RPGO_OK;
 }
 
 /* Batched inlier selection: the groups of one removeOutliers() call are independent (Pcm::findInliers loops over
@@ -1226,7 +1235,7 @@ int rpgo_find_inliers_batch(rpgo_handle* h, int32_t n_groups, const int32_t* gro
   const bool spread = all.active();
   const int world = spread ? h->cfg.world : 1, rank = spread ? h->cfg.rank : 0;
   /* workers: bounded by the scratch they need (the pick logs are CLIQUE_BLOCKS x n ints each) */
-  const size_t per_set = (size_t)CLIQUE_BLOCKS * max_n * 4 + (size_t)max_n * 16;
+  const size_t per_set = (size_t)CLIQUE_BLOCKS * 2 * max_n * 4 + (size_t)max_n * 16;
   int T = (int)std::min<size_t>(8, std::max<size_t>(1, ((size_t)2 << 30) / std::max<size_t>(per_set, 1)));
   T = std::min(T, (n_groups + world - 1) / world);
   while ((int)h->workers.size() < T) {

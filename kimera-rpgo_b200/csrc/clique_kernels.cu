@@ -11,15 +11,28 @@
  *     repeat { pick = S.back(); S = [u in S : u in N(pick)]; icc++ } until S empty
  *     if icc > maxClq { out = scratch buffer; maxClq = icc }
  * Bitset formulation: R = N(v) & {deg >= maxClq}; pick = highest set bit of R; R &= N(pick);
- * icc = 1 + number of picks.  Two exact accelerations:
- *   - bound: steps + |R| + 1 <= maxClq  =>  icc cannot exceed maxClq  =>  the candidate cannot change
- *     the reference's state, stop early;
+ * icc(v) = 1 + number of picks.
+ *
+ * EPOCHS.  maxClq enters a candidate's chain only through the degree filter {deg >= maxClq} (and the skip test, which is
+ * the same set).  Let M be the bound at some point and hi = min{deg(u) : deg(u) >= M}: for every bound M' in [M, hi]
+ * the filter is the same set, so every chain evaluated while the bound stays <= hi is a fixed function icc(v) of the
+ * candidate alone.  The sequential loop therefore decomposes into epochs (start, M):
+ *   (a) v* = the first candidate >= start with icc(v) > hi, if any: everything before it only raised the bound within
+ *       [M, hi]; v* commits (bound icc(v*), filter changes) and the next epoch starts at v* + 1;
+ *   (b) otherwise the loop ends in this epoch and its result is the FIRST candidate attaining max icc (if > M).
+ * Both are order-free searches, so all candidates of an epoch are evaluated concurrently, with two exact prunings on the
+ * chain's upper bound ub = picks so far + |R| + 1:  a chain is abandoned when ub <= hi (cannot be v*) AND (ub, v) cannot
+ * beat the best completed chain so far (cannot be the first arg-max); and everything beyond a known v* is abandoned.
+ * Dense PCM graphs (all degrees far above the clique size) need two epochs — the first ends at the first candidate
+ * because the initial bound -1 admits every vertex — where the round-per-improvement formulation of round 1 needed one
+ * dependent winner chain per improvement (13 at 50k closures).
  *   - window resolution: all picks that fall into the current top 32-bit word of R are resolved by one
  *     warp from a single 32x32 sub-block of the adjacency, then the remaining words are ANDed with all
- *     of those picks' rows in one parallel sweep (one dependent memory round per window, not per pick).
- * The sequential dependence between candidates (maxClq) is honoured by rounds: every candidate is
- * evaluated against a snapshot of maxClq; the first candidate that improves it commits, later
- * candidates are re-evaluated against the new bound (identical to the sequential order of events).
+ *     of those picks' rows in one parallel sweep (one dependent memory round per window, not per pick);
+ *   - verdicts "icc(v) <= hi" are cached across epochs and invalidated only for neighbours of vertices that leave the
+ *     filter.
+ * Multi-GPU: candidates are partitioned over ranks (v mod world); an epoch ends with ONE all-reduce of the two control
+ * words (lowest v*, best chain) over NCCL / the caller's exchange function.
  */
 #include <algorithm>
 #include <climits>
@@ -30,20 +43,30 @@
 
 #include <cooperative_groups.h>
 
+#include "comm.h"
 #include "kernels.cuh"
 
 namespace rpgo {
 
 static constexpr int HEU_THREADS = 128;       /* block size of the clique kernels for n <= HEU_WIDE_N */
 static constexpr int HEU_THREADS_WIDE = 512;  /* wide rows (n > HEU_WIDE_N): 4x the sweep parallelism per chain */
-static constexpr int HEU_WIDE_N = 131072; /* measured: 512-thread blocks lose at 50k (27 vs 15 ms), win at 200k (911 vs 1038 ms) */
-/* measurement build (-DRPGO_CLIQUE_COUNTERS): ctl[1] chains started, ctl[2] windows, ctl[3] adjacency/degree-mask bytes read */
-#ifdef RPGO_CLIQUE_COUNTERS
-#define RPGO_COUNT_BYTES(ctl, x) atomicAdd((ctl) + 3, (unsigned long long)(x))
-#else
-#define RPGO_COUNT_BYTES(ctl, x) ((void)0)
-#endif
+static constexpr int HEU_WIDE_N = 131072;
 static constexpr int HEU_PRE = 13; /* words per thread covered by the sweep prefetch (13 * 128 * 32 = 53k vertices) */
+
+typedef unsigned long long ull;
+
+/* control block of one search (device memory, 8-byte words):
+ *   set e = epoch % 3 at words [4e .. 4e+2]: vstar, best, hi
+ *   [12] row ANDs (statistics: algorithmic bytes = row_ands * n / 8), [13] chains started
+ *   [16..] HeuResult;  byte 256..: saved_sel[block] (which of the block's two pick logs holds its best chain) */
+static constexpr int CTL_ROW_ANDS = 12, CTL_CHAINS = 13, CTL_RESULT = 16, CTL_SAVED_SEL_BYTES = 256;
+static constexpr ull HEU_NONE = ~0ULL;
+
+__device__ __host__ __forceinline__ ull best_key(int icc, int v) {
+  return ((ull)(unsigned)(icc + 1) << 32) | (ull)(0xFFFFFFFFu - (unsigned)v);
+}
+/* can a chain of candidate v whose length is at most ub still matter in this epoch? */
+__device__ __forceinline__ bool heu_relevant(int ub, int v, int hi, ull best) { return ub > hi || best_key(ub, v) > best; }
 
 __global__ void degmask_kernel(const int32_t* __restrict__ deg, int n, int M, uint32_t* mask, int words) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -77,18 +100,29 @@ __device__ __forceinline__ void block_sum_max(int& s, int& m, int* sh) {
   m = tm;
 }
 
-
 static constexpr int HEU_LIST_K = 4;                       /* list elements per thread */
 static constexpr int HEU_LIST_MAX = HEU_LIST_K * HEU_THREADS; /* list mode below this many survivors (any block size) */
+
+/* shared snapshot of the epoch's control words, refreshed by thread 0 between two block barriers */
+struct HeuShared {
+  ull best;
+  int vstar_v; /* candidate index of the lowest known v*, INT_MAX if none */
+  int pad;
+};
+__device__ __forceinline__ void heu_refresh(HeuShared* hs, const ull* cset) {
+  const ull vs = *(volatile const ull*)&cset[0];
+  hs->vstar_v = (vs == HEU_NONE) ? INT_MAX : (int)(vs >> 32);
+  hs->best = *(volatile const ull*)&cset[1];
+}
 
 /* Tail of a greedy chain once at most HEU_LIST_MAX candidates survive: the survivors are written to shared
  * memory as a list in DESCENDING id order, so that "highest set bit of R" becomes "first live list entry"; each
  * pick then costs one adjacency word per live entry instead of a sweep over the whole bitset.  Same picks, same
- * order, same count as the bitset loop.  Returns the number of picks made (-1: a lower candidate already
- * improved, give up; -2: cannot beat M). */
+ * order, same count as the bitset loop.  Returns the number of picks made (-1: a lower candidate already ended the
+ * epoch, give up; -2: the chain cannot matter any more). */
 template <int TH>
 __device__ int heu_list_tail(const uint32_t* __restrict__ bits, int64_t stride32, const uint32_t* R, int top, int cnt,
-                             int steps, int M, int v, unsigned long long* ctl, int32_t* my_picks, int32_t* L, int* sh) {
+                             int steps, int hi, int v, const ull* cset, HeuShared* hs, int32_t* my_picks, int32_t* L, int* sh) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   /* build the list: thread t owns the word range [top - (t+1)*C + 1, top - t*C] scanned from the top */
   const int C = (top + TH) / TH;
@@ -130,9 +164,10 @@ __device__ int heu_list_tail(const uint32_t* __restrict__ bits, int64_t stride32
     alive[k] = pos < cnt;
     u[k] = alive[k] ? L[pos] : 0;
   }
-  int m = cnt, made = 0, iter = 0;
+  ull best = hs->best;
+  int m = cnt, made = 0;
   while (m > 0) {
-    if (steps + made + m + 1 <= M) return -2;
+    if (!heu_relevant(steps + made + m + 1, v, hi, best)) return -2;
     /* first live entry (block-wide minimum position) and live count */
     int first = INT_MAX, live = 0;
 #pragma unroll
@@ -149,7 +184,7 @@ __device__ int heu_list_tail(const uint32_t* __restrict__ bits, int64_t stride32
       sh[wid] = first;
       sh[32 + wid] = live;
     }
-    if (tid == 0) sh[16] = ((++iter & 15) == 0 && (long long)(*(volatile unsigned long long*)ctl >> 32) < (long long)v) ? 1 : 0;
+    if (tid == 0) heu_refresh(hs, cset);
     __syncthreads();
     first = INT_MAX;
     live = 0;
@@ -158,10 +193,11 @@ __device__ int heu_list_tail(const uint32_t* __restrict__ bits, int64_t stride32
       first = min(first, sh[i]);
       live += sh[32 + i];
     }
-    if (sh[16]) return -1;
+    if (hs->vstar_v < v) return -1;
+    best = hs->best;
     m = live;
     if (m == 0) break;
-    if (steps + made + m + 1 <= M) return -2;
+    if (!heu_relevant(steps + made + m + 1, v, hi, best)) return -2;
     const int pick = L[first];
     if (tid == 0) my_picks[steps + made] = pick;
     ++made;
@@ -171,10 +207,7 @@ __device__ int heu_list_tail(const uint32_t* __restrict__ bits, int64_t stride32
       if (alive[k]) {
         const int pos = k * TH + tid;
         if (pos == first) alive[k] = false;
-        else {
-          alive[k] = (prow[u[k] >> 5] >> (u[k] & 31)) & 1u;
-          RPGO_COUNT_BYTES(ctl, 4);
-        }
+        else alive[k] = (prow[u[k] >> 5] >> (u[k] & 31)) & 1u;
       }
     }
     m -= 1; /* refined at the top of the next iteration */
@@ -182,79 +215,56 @@ __device__ int heu_list_tail(const uint32_t* __restrict__ bits, int64_t stride32
   return made;
 }
 
-/* un-mark the cached verdict of every neighbour of the vertices in xs (their filter membership changed) */
-__global__ void undead_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n, const int32_t* __restrict__ xs, int nx,
-                              int32_t* dead_flags) {
-  const int u = xs[blockIdx.x];
-  const int W = (n + 31) / 32;
-  for (int w = threadIdx.x; w < W; w += blockDim.x) {
-    uint32_t r = bits[(size_t)u * stride32 + w];
-    while (r) {
-      const int b = __ffs(r) - 1;
-      r &= r - 1;
-      dead_flags[w * 32 + b] = 0;
-    }
-  }
-  if (threadIdx.x == 0) dead_flags[u] = 0;
-}
-
-/* ctl[0]: packed (candidate << 32 | icc) of the lowest-index improving candidate of this round
- *         (ULLONG_MAX = none).  picks_block: per-block pick log (n ints each). */
+/* One epoch's candidate evaluation for this block: candidates first + blockIdx*vstep, stride gridDim*vstep (vstep > 1
+ * when the candidates are partitioned over ranks).  cset = this epoch's control words {vstar, best, hi}.  The block keeps
+ * two pick logs; *sel says which one holds the block's best completed chain (the other one is written). */
 template <int TH>
 __device__ __forceinline__ void heu_round_body(const uint32_t* __restrict__ bits, int64_t stride32, int n,
                                                const int32_t* __restrict__ deg, const uint32_t* degmask, int first, int vstep,
-                                               int M, unsigned long long* ctl, int32_t* picks_block, int32_t* dead_flags) {
+                                               int M, ull* cset, ull* stats, int32_t* picks_block, int32_t* dead_flags,
+                                               int32_t* saved_sel) {
   extern __shared__ uint32_t R[];
   __shared__ int sh[64];
-  __shared__ int s_abort;
+  __shared__ HeuShared hs;
+  __shared__ int s_flag;
   __shared__ int32_t s_list[HEU_LIST_MAX];
   const int W = (n + 31) / 32;
   const int tid = threadIdx.x;
-  int32_t* my_picks = picks_block + (size_t)blockIdx.x * n;
+  int sel = saved_sel[blockIdx.x]; /* log `sel` is kept, log `1 - sel` is the one being written */
+  const ull hi64 = cset[2];        /* written in the prepare phase, constant during the round */
+  const int hi = hi64 > (ull)INT_MAX ? INT_MAX : (int)hi64;
 
-  /* candidates first, first + vstep, ...: vstep > 1 when the candidates are partitioned over ranks */
   for (long long vv = first + (long long)blockIdx.x * vstep; vv < n; vv += (long long)gridDim.x * vstep) {
     const int v = (int)vv;
-    /* a lower-index candidate already improved: everything from here on is re-evaluated next round */
+    int32_t* my_picks = picks_block + ((size_t)blockIdx.x * 2 + (size_t)(1 - sel)) * n;
     __syncthreads();
-    if (tid == 0) s_abort = ((long long)(*(volatile unsigned long long*)ctl >> 32) < (long long)v) ? 1 : 0;
+    if (tid == 0) heu_refresh(&hs, cset);
     __syncthreads();
-    if (s_abort) return;
-    if (M > deg[v]) continue; /* pruning 1 */
-    if (dead_flags[v]) continue; /* evaluated under an equivalent bound before: cannot improve (see host driver) */
+    if (hs.vstar_v < v) return; /* the epoch ends before v: everything from here on belongs to the next one */
+    ull best = hs.best;
+    if (M > deg[v]) continue;      /* pruning 1 (skip test of the reference) */
+    if (dead_flags[v]) continue;   /* icc(v) <= an earlier epoch's horizon under the same filtered neighbourhood */
     int cnt = 0, top = -1;
     for (int w = tid; w < W; w += blockDim.x) {
       const uint32_t r = bits[(size_t)v * stride32 + w] & degmask[w];
-      RPGO_COUNT_BYTES(ctl, 8);
       R[w] = r;
       cnt += __popc(r);
       if (r) top = w;
     }
     block_sum_max(cnt, top, sh);
-    if (cnt + 1 <= M) {
-      if (tid == 0) dead_flags[v] = 1;
-      continue; /* cannot exceed the bound */
-    }
-#ifdef RPGO_CLIQUE_COUNTERS
-    if (tid == 0) atomicAdd(ctl + 1, 1ULL);
-#endif
     int steps = 0;
-    bool dead = false;
-    int iter = 0;
-    while (cnt > 0) {
-      if (steps + cnt + 1 <= M) { dead = true; break; }
+    bool dead = !heu_relevant(cnt + 1, v, hi, best);
+    if (tid == 0 && !dead) atomicAdd(&stats[CTL_CHAINS - CTL_ROW_ANDS], 1ULL);
+    while (!dead && cnt > 0) {
       if (cnt <= HEU_LIST_MAX) {
-        const int made = heu_list_tail<TH>(bits, stride32, R, top, cnt, steps, M, v, ctl, my_picks, s_list, sh);
+        const int made = heu_list_tail<TH>(bits, stride32, R, top, cnt, steps, hi, v, cset, &hs, my_picks, s_list, sh);
         if (made == -1) return;
         if (made == -2) { dead = true; break; }
         steps += made;
         break;
       }
-      if (tid == 0) s_abort = ((++iter & 7) == 0 && (long long)(*(volatile unsigned long long*)ctl >> 32) < (long long)v) ? 1 : 0;
+      if (tid == 0) heu_refresh(&hs, cset);
       const int t = top;
-#ifdef RPGO_CLIQUE_COUNTERS
-      if (tid == 0) atomicAdd(ctl + 2, 1ULL);
-#endif
       const uint32_t T = R[t];
       const int lane = tid & 31;
       /* every warp resolves the window redundantly from the same 32x32 adjacency block (no block barrier
@@ -262,7 +272,6 @@ __device__ __forceinline__ void heu_round_body(const uint32_t* __restrict__ bits
        * that both dependent global accesses overlap: one memory round trip per window */
       uint32_t rw = 0;
       if ((T >> lane) & 1u) rw = bits[(size_t)(t * 32 + lane) * stride32 + t];
-      if (tid < 32 && ((T >> lane) & 1u)) RPGO_COUNT_BYTES(ctl, 4);
       const int nT = __popc(T);
       uint32_t pre[4][HEU_PRE]; /* up to 4 candidate rows x HEU_PRE words per thread are prefetched */
       const bool prefetch = (nT <= 4) && (t <= HEU_PRE * TH);
@@ -276,7 +285,6 @@ __device__ __forceinline__ void heu_round_body(const uint32_t* __restrict__ bits
           for (int k = 0; k < HEU_PRE; ++k) {
             const int w = tid + k * TH;
             pre[c][k] = (b >= 0 && w < t) ? bits[(size_t)(t * 32 + b) * stride32 + w] : 0xffffffffu;
-            if (b >= 0 && w < t) RPGO_COUNT_BYTES(ctl, 4);
           }
         }
       }
@@ -290,8 +298,9 @@ __device__ __forceinline__ void heu_round_body(const uint32_t* __restrict__ bits
         if (tid == 0) my_picks[steps + k0] = t * 32 + b;
         ++k0;
       }
-      __syncthreads(); /* all warps have read R[t] / s_abort is visible */
-      if (s_abort) return;
+      __syncthreads(); /* all warps have read R[t]; the control snapshot is visible */
+      if (hs.vstar_v < v) return;
+      best = hs.best;
       if (tid == 0) R[t] = 0;
       steps += __popc(P);
       cnt = 0;
@@ -320,15 +329,21 @@ __device__ __forceinline__ void heu_round_body(const uint32_t* __restrict__ bits
           }
         }
       } else {
+        /* many picks in this window: AND all of their rows into every surviving word.  The row loads of one word do
+         * not depend on each other (no early exit), four are kept in flight per thread */
         for (int w = tid; w < t; w += blockDim.x) {
           uint32_t r = R[w];
           if (r) {
             uint32_t q = P;
-            while (q && r) {
-              const int b = 31 - __clz(q);
-              q &= ~(1u << b);
-              r &= bits[(size_t)(t * 32 + b) * stride32 + w];
-              RPGO_COUNT_BYTES(ctl, 4);
+            while (q) {
+              uint32_t m4[4];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const int b = q ? 31 - __clz(q) : -1;
+                if (b >= 0) q &= ~(1u << b);
+                m4[c] = b >= 0 ? bits[(size_t)(t * 32 + b) * stride32 + w] : 0xffffffffu;
+              }
+              r &= (m4[0] & m4[1]) & (m4[2] & m4[3]);
             }
             R[w] = r;
             cnt += __popc(r);
@@ -337,76 +352,64 @@ __device__ __forceinline__ void heu_round_body(const uint32_t* __restrict__ bits
         }
       }
       block_sum_max(cnt, top, sh);
+      if (!heu_relevant(steps + cnt + 1, v, hi, best)) dead = true;
     }
+    if (tid == 0) atomicAdd(&stats[0], (ull)(1 + steps));
     if (dead) {
-      if (tid == 0) dead_flags[v] = 1;
+      if (tid == 0) dead_flags[v] = 1; /* icc(v) <= hi: stays true for every later bound while the neighbourhood filter is unchanged */
       continue;
     }
     const int icc = steps + 1;
-    if (icc > M) {
-      if (tid == 0) atomicMin(ctl, ((unsigned long long)(unsigned)v << 32) | (unsigned)icc);
-      return; /* later candidates of this block are > v: re-evaluated next round */
+    if (icc > hi) {
+      /* ends the epoch (unless a lower candidate does): the log stays in the buffer being written */
+      if (tid == 0) atomicMin(&cset[0], ((ull)(unsigned)v << 32) | (unsigned)icc);
+      return; /* later candidates of this block are > v: they belong to the next epoch */
     }
-    if (tid == 0) dead_flags[v] = 1; /* completed chain that did not beat M */
+    __syncthreads();
+    if (tid == 0) {
+      const ull key = best_key(icc, v);
+      const ull old = atomicMax(&cset[1], key);
+      s_flag = old < key ? 1 : 0;
+      dead_flags[v] = 1;
+    }
+    __syncthreads();
+    if (s_flag) { /* best completed chain so far: keep its log, write the following ones into the other buffer */
+      sel = 1 - sel;
+      if (tid == 0) saved_sel[blockIdx.x] = sel;
+    }
   }
 }
 
-template <int TH>
-__global__ void __launch_bounds__(TH) heu_round_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n,
-                                                                const int32_t* __restrict__ deg,
-                                                                const uint32_t* __restrict__ degmask, int first, int vstep,
-                                                                int M, unsigned long long* ctl, int32_t* picks_block,
-                                                                int32_t* dead_flags) {
-  heu_round_body<TH>(bits, stride32, n, deg, degmask, first, vstep, M, ctl, picks_block, dead_flags);
-}
-
-/* All rounds of one search in ONE cooperative launch (single-rank searches): the bound update, the winner's pick log and
- * the invalidation of cached verdicts move onto the device, separated by grid-wide barriers, so a search costs one launch
- * and one host synchronisation instead of ~7 API calls per round.  Same rounds, same order of events as the host loop. */
-struct HeuResult {
-  int M, winner, winner_M, winner_icc, rounds, pad;
-};
-
-template <int TH>
-__global__ void __launch_bounds__(TH) heu_persistent_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n,
-                                                                     const int32_t* __restrict__ deg, uint32_t* degmask,
-                                                                     int first, int maxclq0, unsigned long long* ctl,
-                                                                     int32_t* picks_block, int32_t* dead_flags,
-                                                                     int32_t* picks_out, HeuResult* result) {
-  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+/* Epoch preparation, executed by the whole grid: (1) cached verdicts of the neighbours of every vertex that left the
+ * degree filter (M_prev <= deg < M) are dropped, (2) the filter mask of bound M, (3) hi = min{deg >= M}. */
+__device__ __forceinline__ void heu_prepare_body(const uint32_t* __restrict__ bits, int64_t stride32, int n,
+                                                 const int32_t* __restrict__ deg, int M_prev, int M, bool invalidate,
+                                                 uint32_t* degmask, ull* cset, int32_t* dead_flags) {
   const int W = (n + 31) / 32;
   const int tid = threadIdx.x;
   const long long gtid = (long long)blockIdx.x * blockDim.x + tid, gthreads = (long long)gridDim.x * blockDim.x;
-  int M = maxclq0, start = first < 0 ? 0 : first;
-  int winner = -1, winner_M = 0, winner_icc = 0, rounds = 0;
-  while (start < n) {
-    /* degree filter of this bound, control word */
-    for (long long w = gtid; w < W; w += gthreads) {
-      uint32_t m = 0;
+  int lo = INT_MAX;
+  for (long long w = gtid; w < W; w += gthreads) {
+    uint32_t m = 0;
 #pragma unroll 4
-      for (int b = 0; b < 32; ++b) {
-        const int u = (int)w * 32 + b;
-        if (u < n && deg[u] >= M) m |= 1u << b;
+    for (int b = 0; b < 32; ++b) {
+      const int u = (int)w * 32 + b;
+      if (u < n) {
+        const int d = deg[u];
+        if (d >= M) {
+          m |= 1u << b;
+          lo = min(lo, d);
+        }
       }
-      degmask[w] = m;
     }
-    if (gtid == 0) ctl[0] = ~0ULL;
-    grid.sync();
-    heu_round_body<TH>(bits, stride32, n, deg, degmask, start, 1, M, ctl, picks_block, dead_flags);
-    grid.sync();
-    ++rounds;
-    const unsigned long long c = *(volatile unsigned long long*)ctl;
-    if (c == ~0ULL) break;
-    const int v = (int)(c >> 32), icc = (int)(c & 0xffffffffu);
-    /* the winner's block keeps its pick log */
-    if ((int)blockIdx.x == (v - start) % (int)gridDim.x) {
-      const int32_t* my_picks = picks_block + (size_t)blockIdx.x * n;
-      for (int k = tid; k < icc - 1; k += blockDim.x) picks_out[k] = my_picks[k];
-    }
-    /* a vertex with M <= deg < icc leaves the degree filter: cached verdicts of its neighbours are no longer valid */
+    degmask[w] = m;
+  }
+  lo = __reduce_min_sync(0xffffffffu, lo);
+  if ((tid & 31) == 0 && lo != INT_MAX) atomicMin(&cset[2], (ull)lo);
+  if (invalidate) {
     for (int u = blockIdx.x; u < n; u += gridDim.x) {
       const int d = deg[u];
-      if (d >= M && d < icc) {
+      if (d >= M_prev && d < M) {
         for (int w = tid; w < W; w += blockDim.x) {
           uint32_t r = bits[(size_t)u * stride32 + w];
           while (r) {
@@ -418,20 +421,109 @@ __global__ void __launch_bounds__(TH) heu_persistent_kernel(const uint32_t* __re
         if (tid == 0) dead_flags[u] = 0;
       }
     }
-    winner = v;
-    winner_M = M;
-    winner_icc = icc;
-    M = icc;
-    start = v + 1;
+  }
+}
+
+__global__ void heu_prepare_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n, const int32_t* __restrict__ deg,
+                                   int M_prev, int M, int invalidate, uint32_t* degmask, ull* cset, int32_t* dead_flags) {
+  heu_prepare_body(bits, stride32, n, deg, M_prev, M, invalidate != 0, degmask, cset, dead_flags);
+}
+
+template <int TH>
+__global__ void __launch_bounds__(TH) heu_round_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n,
+                                                                const int32_t* __restrict__ deg,
+                                                                const uint32_t* __restrict__ degmask, int first, int vstep,
+                                                                int M, ull* ctl, int32_t* picks_block, int32_t* dead_flags) {
+  heu_round_body<TH>(bits, stride32, n, deg, degmask, first, vstep, M, ctl, ctl + CTL_ROW_ANDS, picks_block, dead_flags,
+                     (int32_t*)((char*)ctl + CTL_SAVED_SEL_BYTES));
+}
+
+/* copy the pick log of candidate `v` (evaluated by block `blk`) to picks_out: which = 0 the log being written when the
+ * block stopped (a v* chain), 1 the block's saved best chain */
+__global__ void heu_copy_log_kernel(const int32_t* __restrict__ picks_block, const ull* ctl, int blk, int which, int n, int K,
+                                    int32_t* picks_out) {
+  const int32_t* saved_sel = (const int32_t*)((const char*)ctl + CTL_SAVED_SEL_BYTES);
+  const int sel = saved_sel[blk];
+  const int32_t* src = picks_block + ((size_t)blk * 2 + (size_t)(which ? sel : 1 - sel)) * n;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) picks_out[k] = src[k];
+}
+
+/* All epochs of one search in ONE cooperative launch (single-rank searches): preparation, candidate evaluation and the
+ * epoch decision are separated by grid-wide barriers, so a search costs one launch and one host synchronisation. */
+struct HeuResult {
+  int M, winner, winner_M, winner_icc, epochs, pad;
+};
+
+template <int TH>
+__global__ void __launch_bounds__(TH) heu_persistent_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n,
+                                                                     const int32_t* __restrict__ deg, uint32_t* degmask,
+                                                                     int first, int maxclq0, ull* ctl,
+                                                                     int32_t* picks_block, int32_t* dead_flags,
+                                                                     int32_t* picks_out) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const int tid = threadIdx.x;
+  const long long gtid = (long long)blockIdx.x * blockDim.x + tid;
+  int32_t* saved_sel = (int32_t*)((char*)ctl + CTL_SAVED_SEL_BYTES);
+  HeuResult* result = (HeuResult*)(ctl + CTL_RESULT);
+  int M = maxclq0, M_prev = maxclq0, start = first < 0 ? 0 : first;
+  int winner = -1, winner_M = 0, winner_icc = 0, epochs = 0;
+  /* the host initialised set 0 completely and the horizon word of set 1 */
+  while (start < n) {
+    ull* cset = ctl + 4 * (epochs % 3);
+    heu_prepare_body(bits, stride32, n, deg, M_prev, M, epochs > 0, degmask, cset, dead_flags);
     grid.sync();
+    heu_round_body<TH>(bits, stride32, n, deg, degmask, start, 1, M, cset, ctl + CTL_ROW_ANDS, picks_block, dead_flags, saved_sel);
+    grid.sync();
+    const ull vs = *(volatile ull*)&cset[0];
+    const ull bs = *(volatile ull*)&cset[1];
+    const int e = epochs++;
+    if (vs != HEU_NONE) {
+      const int v = (int)(vs >> 32), icc = (int)(vs & 0xffffffffu);
+      if ((int)blockIdx.x == (v - start) % (int)gridDim.x) {
+        const int32_t* src = picks_block + ((size_t)blockIdx.x * 2 + (size_t)(1 - saved_sel[blockIdx.x])) * n;
+        for (int k = tid; k < icc - 1; k += blockDim.x) picks_out[k] = src[k];
+      }
+      winner = v;
+      winner_M = M;
+      winner_icc = icc;
+      M_prev = M;
+      M = icc;
+      start = v + 1;
+      if (gtid == 0) {
+        ull* nx = ctl + 4 * ((e + 1) % 3);
+        nx[0] = HEU_NONE;
+        nx[1] = best_key(M, 0); /* the largest key of length M: a completed chain has to be strictly longer to beat it */
+        ctl[4 * ((e + 2) % 3) + 2] = HEU_NONE;
+      }
+      continue; /* the next prepare phase only touches set (e+1)%3's horizon word, reset one epoch earlier */
+    }
+    const int icc_b = (int)(bs >> 32) - 1, v_b = (int)(0xFFFFFFFFu - (unsigned)(bs & 0xffffffffu));
+    if (icc_b > M) {
+      if ((int)blockIdx.x == (v_b - start) % (int)gridDim.x) {
+        const int32_t* src = picks_block + ((size_t)blockIdx.x * 2 + (size_t)saved_sel[blockIdx.x]) * n;
+        for (int k = tid; k < icc_b - 1; k += blockDim.x) picks_out[k] = src[k];
+      }
+      winner = v_b;
+      winner_M = M;
+      winner_icc = icc_b;
+      M = icc_b;
+    }
+    break;
   }
   if (gtid == 0) {
     result->M = M;
     result->winner = winner;
     result->winner_M = winner_M;
     result->winner_icc = winner_icc;
-    result->rounds = rounds;
+    result->epochs = epochs;
   }
+}
+
+/* (vstar, best) -> (vstar or LLONG_MAX, -best): one MIN all-reduce then yields the lowest v* and the best chain */
+__global__ void heu_pack_keys_kernel(const ull* cset, long long* out) {
+  const ull vs = cset[0];
+  out[0] = vs == HEU_NONE ? LLONG_MAX : (long long)vs;
+  out[1] = -(long long)cset[1];
 }
 
 /* elimination step of every vertex of the winner's initial list:
@@ -506,7 +598,7 @@ __global__ void heu_select_kernel(int n, int K, const int32_t* __restrict__ elim
  * entries of the reference's returned buffer; true_out_host (optional) the greedy clique itself. */
 int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_t* deg, int first, int maxclq0,
                      CliqueScratch s, int32_t* ids_out_host, int32_t* true_out_host, int64_t* launches,
-                     cudaStream_t st, CliqueShard cs) {
+                     cudaStream_t st, CliqueShard cs, CliqueStats* stats_out) {
   const bool sharded = cs.active();
   const int world = sharded ? cs.world : 1, rank = sharded ? cs.rank : 0;
   if (n <= 0) return -1;
@@ -517,174 +609,180 @@ int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_
   if (attr_set.first()) {
     cudaFuncSetAttribute(heu_round_kernel<HEU_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(heu_round_kernel<HEU_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(heu_persistent_kernel<HEU_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(heu_persistent_kernel<HEU_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   }
   static const char* wide_env = getenv("RPGO_CLIQUE_WIDE"); /* A/B knob: 0 / 1 forces the block size */
   const bool wide = wide_env ? (wide_env[0] == '1') : (n > HEU_WIDE_N);
   const int threads = wide ? HEU_THREADS_WIDE : HEU_THREADS;
-  /* "dead" cache: a candidate that could not beat bound M cannot beat any M' >= M as long as its filtered
-   * neighbourhood {u : deg(u) >= M} is unchanged, i.e. as long as no vertex has M <= deg < M'.  The host checks
-   * that on the sorted degree list at every bound change and clears the cache otherwise. */
-  const bool trace = getenv("RPGO_CLIQUE_TRACE") != nullptr;
+  static const bool trace = getenv("RPGO_CLIQUE_TRACE") != nullptr;
+  static const bool host_loop = getenv("RPGO_CLIQUE_HOSTLOOP") != nullptr;
   auto now_ms = []() {
     timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
   };
   const double t_begin = now_ms();
-  double t_round0 = 0;
-  static const bool host_loop = getenv("RPGO_CLIQUE_HOSTLOOP") != nullptr;
-  const bool persistent = !sharded && !trace && !host_loop;
-  std::vector<int32_t> hdeg;
-  CUCHECK(cudaMemsetAsync(s.elim, 0, sizeof(int32_t) * n, st));
-  if (!persistent) { /* the host loop needs the degrees for the cache invalidation */
-    hdeg.resize(n);
-    CUCHECK(cudaMemcpyAsync(hdeg.data(), deg, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-    CUCHECK(cudaStreamSynchronize(st));
-  }
-  std::vector<int32_t> changed; /* vertices whose filter membership changes between two bounds */
-  int M = maxclq0;
-  int winner = -1, winner_M = 0, winner_icc = 0, winner_block = 0;
-  bool winner_local = true;
+  ull* ctl = (ull*)s.ctl;
   int start = first < 0 ? 0 : first;
-  if (persistent) {
-    /* single rank: all rounds in one cooperative launch */
-    static PerDeviceOnce attr2;
-    if (attr2.first()) {
-      cudaFuncSetAttribute(heu_persistent_kernel<HEU_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      cudaFuncSetAttribute(heu_persistent_kernel<HEU_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    }
+  int M = maxclq0, M_prev = maxclq0;
+  int winner = -1, winner_M = 0, winner_icc = 0, epochs = 0;
+  if (start >= n) return M;
+
+  /* grid: one block per candidate up to the scratch capacity; small groups take a slice of the machine so that
+   * independent searches (batched entry point) run side by side */
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int mine = (n - start + world - 1) / world; /* candidates of this rank (upper bound) */
+  int grid = (int)s.rwork_blocks;
+  {
+    const int want = std::max(64, (mine + 7) / 8);
+    if (grid > want) grid = want;
+    if (grid > mine) grid = std::max(1, mine);
+  }
+
+  /* control block: set 0 ready for epoch 0, horizon word of set 1, statistics, saved_sel */
+  {
+    ull init[16];
+    for (int i = 0; i < 16; ++i) init[i] = 0;
+    init[0] = HEU_NONE;
+    init[1] = best_key(M, 0); /* the largest key of length M: only strictly longer chains beat it */
+    init[2] = HEU_NONE;
+    init[4 + 2] = HEU_NONE;
+    CUCHECK(cudaMemcpyAsync(ctl, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    CUCHECK(cudaMemsetAsync((char*)ctl + CTL_SAVED_SEL_BYTES, 0, sizeof(int32_t) * (size_t)s.rwork_blocks, st));
+    CUCHECK(cudaMemsetAsync(s.elim, 0, sizeof(int32_t) * n, st));
+  }
+
+  bool done = false;
+  bool winner_local = true;
+  if (!sharded && !host_loop) {
+    /* single rank: all epochs in one cooperative launch */
     const void* pk = wide ? (const void*)heu_persistent_kernel<HEU_THREADS_WIDE> : (const void*)heu_persistent_kernel<HEU_THREADS>;
-    int dev = 0, sms = 0, bps = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int bps = 0;
     if (wide) CUCHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, heu_persistent_kernel<HEU_THREADS_WIDE>, HEU_THREADS_WIDE, smem));
     else CUCHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, heu_persistent_kernel<HEU_THREADS>, HEU_THREADS, smem));
     if (bps >= 1) {
-      int grid = bps * sms;
-      if (grid > (int)s.rwork_blocks) grid = (int)s.rwork_blocks;
-      /* small groups take a slice of the machine so that independent searches (batched entry point) run side by side */
-      const int want = std::max(64, (n - start + 7) / 8);
-      if (grid > want) grid = want;
-      if (grid > n - start) grid = std::max(1, n - start);
-      HeuResult* d_res = (HeuResult*)((unsigned long long*)s.ctl + 4);
+      int cgrid = std::min(grid, bps * sms);
       const uint32_t* a_bits = bits;
       int64_t a_stride = stride32;
       int a_n = n, a_first = start, a_M = maxclq0;
       const int32_t* a_deg = deg;
       uint32_t* a_degmask = s.degmask;
-      unsigned long long* a_ctl = (unsigned long long*)s.ctl;
+      ull* a_ctl = ctl;
       int32_t* a_rwork = (int32_t*)s.rwork;
       int32_t* a_elim = s.elim;
       int32_t* a_picks = s.picks;
-      void* args[] = {&a_bits, &a_stride, &a_n, &a_deg, &a_degmask, &a_first, &a_M, &a_ctl, &a_rwork, &a_elim, &a_picks, &d_res};
-      CUCHECK(cudaLaunchCooperativeKernel(pk, dim3(grid), dim3(threads), args, smem, st));
+      void* args[] = {&a_bits, &a_stride, &a_n, &a_deg, &a_degmask, &a_first, &a_M, &a_ctl, &a_rwork, &a_elim, &a_picks};
+      CUCHECK(cudaLaunchCooperativeKernel(pk, dim3(cgrid), dim3(threads), args, smem, st));
       *launches += 1;
       HeuResult hr;
-      CUCHECK(cudaMemcpyAsync(&hr, d_res, sizeof(hr), cudaMemcpyDeviceToHost, st));
+      CUCHECK(cudaMemcpyAsync(&hr, ctl + CTL_RESULT, sizeof(hr), cudaMemcpyDeviceToHost, st));
       CUCHECK(cudaStreamSynchronize(st));
       M = hr.M;
       winner = hr.winner;
       winner_M = hr.winner_M;
       winner_icc = hr.winner_icc;
-      start = n; /* the host loop below is skipped */
+      epochs = hr.epochs;
+      done = true;
     }
   }
-  std::vector<int32_t> picks_host;
-  const int grid_cap = (int)s.rwork_blocks;
-  unsigned long long h_ctl;
-  if (trace) fprintf(stderr, "[clique] setup (degree copy + sort) %.3f ms\n", now_ms() - t_begin);
-  while (start < n) {
-    t_round0 = now_ms();
-    const unsigned long long none = ~0ULL;
-    const unsigned long long init3[4] = {none, 0ULL, 0ULL, 0ULL};
-    CUCHECK(cudaMemcpyAsync(s.ctl, init3, sizeof(init3), cudaMemcpyHostToDevice, st));
-    degmask_kernel<<<(W + 127) / 128, 128, 0, st>>>(deg, n, M, s.degmask, W);
-    /* candidates of this rank: v = start (mod nothing) for one GPU, v = rank (mod world) when partitioned */
+  /* host-driven epochs: the multi-rank form (one all-reduce of the control words per epoch) and the fallback */
+  int winner_owner = rank;
+  while (!done && start < n) {
+    const double t0 = now_ms();
+    if (epochs > 0) {
+      ull init[3] = {HEU_NONE, best_key(M, 0), HEU_NONE};
+      CUCHECK(cudaMemcpyAsync(ctl, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    }
+    heu_prepare_kernel<<<std::min(4 * sms, std::max(1, (n + 127) / 128)), 128, 0, st>>>(bits, stride32, n, deg, M_prev, M, epochs > 0 ? 1 : 0,
+                                                                                        s.degmask, ctl, s.elim);
+    /* candidates of this rank: v = rank (mod world), starting at or after `start` */
     const int v0 = start + (((rank - start) % world) + world) % world;
-    int grid = (n - v0 + world - 1) / world;
-    if (grid > grid_cap) grid = grid_cap;
-    if (grid > 0) {
+    int egrid = (n - v0 + world - 1) / world;
+    if (egrid > grid) egrid = grid;
+    if (egrid > 0) {
       if (wide)
-        heu_round_kernel<HEU_THREADS_WIDE><<<grid, HEU_THREADS_WIDE, smem, st>>>(bits, stride32, n, deg, s.degmask, v0, world, M,
-                                                                             (unsigned long long*)s.ctl, (int32_t*)s.rwork, s.elim);
+        heu_round_kernel<HEU_THREADS_WIDE><<<egrid, HEU_THREADS_WIDE, smem, st>>>(bits, stride32, n, deg, s.degmask, v0, world, M, ctl,
+                                                                              (int32_t*)s.rwork, s.elim);
       else
-        heu_round_kernel<HEU_THREADS><<<grid, HEU_THREADS, smem, st>>>(bits, stride32, n, deg, s.degmask, v0, world, M,
-                                                                     (unsigned long long*)s.ctl, (int32_t*)s.rwork, s.elim);
+        heu_round_kernel<HEU_THREADS><<<egrid, HEU_THREADS, smem, st>>>(bits, stride32, n, deg, s.degmask, v0, world, M, ctl,
+                                                                      (int32_t*)s.rwork, s.elim);
       *launches += 1;
     }
     *launches += 1;
-    CUCHECK(cudaMemcpyAsync(&h_ctl, s.ctl, sizeof(h_ctl), cudaMemcpyDeviceToHost, st));
-    CUCHECK(cudaStreamSynchronize(st));
-    bool local_winner = true;
-    if (sharded) {
-      /* incumbent exchange: the lowest-index improving candidate over all ranks wins the round */
-      const unsigned long long mine = h_ctl;
-      long long key = (h_ctl == none) ? LLONG_MAX : (long long)h_ctl;
-      if (cs.xchg(RPGO_XCHG_MIN_I64, &key, 1, 0) != 0) return -3;
-      h_ctl = (key == LLONG_MAX) ? none : (unsigned long long)key;
-      local_winner = (h_ctl == mine);
+    /* epoch decision: lowest v* and best chain over all ranks */
+    long long key[2];
+    if (sharded && cs.comm) {
+      /* on the device: -best so that one MIN all-reduce serves both words */
+      heu_pack_keys_kernel<<<1, 1, 0, st>>>(ctl, (long long*)(ctl + 8));
+      if (comm_allreduce_i64_device(cs.comm, (long long*)(ctl + 8), 2, false, st) != 0) return -3;
+      CUCHECK(cudaMemcpyAsync(key, ctl + 8, sizeof(key), cudaMemcpyDeviceToHost, st));
+      CUCHECK(cudaStreamSynchronize(st));
+    } else {
+      ull h[2];
+      CUCHECK(cudaMemcpyAsync(h, ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
+      CUCHECK(cudaStreamSynchronize(st));
+      key[0] = h[0] == HEU_NONE ? LLONG_MAX : (long long)h[0];
+      key[1] = -(long long)h[1];
+      if (sharded && cs.xchg(RPGO_XCHG_MIN_I64, key, 2, 0) != 0) return -3;
     }
-    if (trace) {
-      fprintf(stderr, "[clique] rank %d round kernel+sync %.3f ms\n", rank, now_ms() - t_round0);
-      unsigned long long c[4];
-      cudaMemcpy(c, s.ctl, sizeof(c), cudaMemcpyDeviceToHost);
-      fprintf(stderr, "[clique] round start=%d M=%d grid=%d -> improver=%lld icc=%d | chains started %llu, windows %llu, bytes %llu\n", start, M, grid,
-              h_ctl == none ? -1LL : (long long)(h_ctl >> 32), (int)(h_ctl & 0xffffffffu), c[1], c[2], c[3]);
+    ++epochs;
+    if (trace) fprintf(stderr, "[clique] rank %d epoch %d start=%d M=%d grid=%d: %.3f ms\n", rank, epochs, start, M, egrid, now_ms() - t0);
+    int which = -1;
+    if (key[0] != LLONG_MAX) {
+      winner = (int)((ull)key[0] >> 32);
+      winner_icc = (int)((ull)key[0] & 0xffffffffu);
+      which = 0;
+    } else {
+      const ull bs = (ull)(-key[1]);
+      const int icc_b = (int)(bs >> 32) - 1;
+      if (icc_b > M) {
+        winner = (int)(0xFFFFFFFFu - (unsigned)(bs & 0xffffffffu));
+        winner_icc = icc_b;
+        which = 1;
+      }
     }
-    if (h_ctl == none) break;
-    winner = (int)(h_ctl >> 32);
-    winner_icc = (int)(h_ctl & 0xffffffffu);
-    winner_M = M;
-    winner_local = local_winner;
-    if (local_winner) {
-      winner_block = ((winner - v0) / world) % grid;
-      /* keep the winner's pick log (its block may be reused next round) */
-      CUCHECK(cudaMemcpyAsync(s.picks, (int32_t*)s.rwork + (size_t)winner_block * n,
-                              sizeof(int32_t) * (size_t)(winner_icc - 1 > 0 ? winner_icc - 1 : 0), cudaMemcpyDeviceToDevice, st));
-    }
-    {
-      /* any vertex with M <= deg < winner_icc changes the filter: cached verdicts are no longer valid */
-      changed.clear();
-      for (int u = 0; u < n && changed.size() <= 4096; ++u)
-        if (hdeg[u] >= M && hdeg[u] < winner_icc) changed.push_back(u);
-      const int nx = (int)changed.size();
-      if (nx > 4096) {
-        CUCHECK(cudaMemsetAsync(s.elim, 0, sizeof(int32_t) * n, st));
-      } else if (nx > 0) {
-        /* only candidates adjacent to one of those vertices see a different filtered neighbourhood */
-        CUCHECK(cudaMemcpyAsync(s.result, changed.data(), sizeof(int32_t) * nx, cudaMemcpyHostToDevice, st));
-        CUCHECK(cudaStreamSynchronize(st)); /* `changed` is reused next round */
-        undead_kernel<<<nx, 128, 0, st>>>(bits, stride32, n, s.result, nx, s.elim);
+    if (which >= 0) {
+      winner_M = M;
+      winner_owner = winner % world;
+      winner_local = !sharded || winner_owner == rank;
+      if (winner_local && winner_icc > 1) {
+        const int blk = ((winner - v0) / world) % egrid;
+        heu_copy_log_kernel<<<std::min(64, (winner_icc + 255) / 256), 256, 0, st>>>((const int32_t*)s.rwork, ctl, blk, which, n, winner_icc - 1,
+                                                                                   s.picks);
         *launches += 1;
       }
     }
-    M = winner_icc;
+    if (which >= 0) {
+      M_prev = M;
+      M = winner_icc;
+    }
+    if (which != 0) break; /* no candidate crossed the horizon: the loop ends in this epoch */
     start = winner + 1;
+  }
+  if (stats_out) {
+    ull st2[2] = {0, 0};
+    CUCHECK(cudaMemcpyAsync(st2, ctl + CTL_ROW_ANDS, sizeof(st2), cudaMemcpyDeviceToHost, st));
+    CUCHECK(cudaStreamSynchronize(st));
+    stats_out->row_ands = (long long)st2[0];
+    stats_out->chains = (long long)st2[1];
+    stats_out->epochs = epochs;
   }
   if (winner < 0) return M; /* no candidate improved on maxclq0 (incremental mode) */
   const double t_replay = now_ms();
-  if (trace) fprintf(stderr, "[clique] rounds done at %.3f ms\n", t_replay - t_begin);
+  if (trace) fprintf(stderr, "[clique] %d epochs done at %.3f ms\n", epochs, t_replay - t_begin);
 
   const int K = winner_icc - 1;
-  if (!winner_local) {
-    /* the final winning chain ran on another rank: replay that one candidate here (same bound, same filter) to get
-     * its pick log; intermediate winners only moved the bound and need no log */
-    const unsigned long long init3[4] = {~0ULL, 0ULL, 0ULL, 0ULL};
-    CUCHECK(cudaMemcpyAsync(s.ctl, init3, sizeof(init3), cudaMemcpyHostToDevice, st));
-    CUCHECK(cudaMemsetAsync(s.elim + winner, 0, sizeof(int32_t), st));
-    degmask_kernel<<<(W + 127) / 128, 128, 0, st>>>(deg, n, winner_M, s.degmask, W);
-    if (wide)
-      heu_round_kernel<HEU_THREADS_WIDE><<<1, HEU_THREADS_WIDE, smem, st>>>(bits, stride32, n, deg, s.degmask, winner, n, winner_M,
-                                                                        (unsigned long long*)s.ctl, (int32_t*)s.rwork, s.elim);
-    else
-      heu_round_kernel<HEU_THREADS><<<1, HEU_THREADS, smem, st>>>(bits, stride32, n, deg, s.degmask, winner, n, winner_M,
-                                                                (unsigned long long*)s.ctl, (int32_t*)s.rwork, s.elim);
-    *launches += 2;
-    CUCHECK(cudaMemcpyAsync(s.picks, (int32_t*)s.rwork, sizeof(int32_t) * (size_t)(K > 0 ? K : 0), cudaMemcpyDeviceToDevice, st));
-  }
-  picks_host.resize(K > 0 ? K : 1);
-  if (K > 0) CUCHECK(cudaMemcpyAsync(picks_host.data(), s.picks, sizeof(int32_t) * K, cudaMemcpyDeviceToHost, st));
+  std::vector<int32_t> picks_host(K > 0 ? K : 1);
+  if (K > 0 && (!sharded || winner_local)) CUCHECK(cudaMemcpyAsync(picks_host.data(), s.picks, sizeof(int32_t) * K, cudaMemcpyDeviceToHost, st));
   CUCHECK(cudaStreamSynchronize(st));
+  if (sharded && K > 0) {
+    /* the winning chain ran on rank winner_owner: its pick log goes to everybody */
+    if (cs.xchg(RPGO_XCHG_BCAST_I32, picks_host.data(), K, winner_owner) != 0) return -3;
+    if (!winner_local) CUCHECK(cudaMemcpyAsync(s.picks, picks_host.data(), sizeof(int32_t) * K, cudaMemcpyHostToDevice, st));
+  }
   if (true_out_host) {
     true_out_host[0] = winner;
     for (int k = 0; k < K; ++k) true_out_host[1 + k] = picks_host[k];

@@ -99,9 +99,16 @@ struct CliqueScratch {
   int32_t* picks;           /* n */
   int32_t* elim;            /* n */
   int32_t* result;          /* n */
-  long long* ctl;           /* control words: [0] first improver, [1] its icc, ... */
-  uint32_t* rwork;          /* per-block working sets: grid x stride32 */
+  long long* ctl;           /* control block (clique_kernels.cu): epoch words, statistics, result, per-block log selectors */
+  uint32_t* rwork;          /* per-block pick logs: rwork_blocks x 2 x n ints */
   int64_t rwork_blocks;
+};
+/* bytes the control block needs for `blocks` thread blocks */
+inline size_t clique_ctl_bytes(int64_t blocks) { return 256 + (size_t)blocks * 4 + 64; }
+struct CliqueStats {
+  long long row_ands = 0; /* adjacency-row ANDs of the heuristic: algorithmic bytes = row_ands * n / 8 */
+  long long chains = 0;   /* greedy chains started */
+  int epochs = 0;
 };
 /* candidate partition of the clique searches over ranks; the incumbent is combined over the handle's NCCL communicator
  * (rpgo_comm_init) or, when the caller brings its own collective, the host function of rpgo_set_exchange */
@@ -118,7 +125,7 @@ struct CliqueShard {
 };
 int clique_heuristic(const uint32_t* bits, int64_t stride32, int n, const int32_t* deg, int first, int maxclq0,
                      CliqueScratch s, int32_t* ids_out_host, int32_t* true_out_host, int64_t* launches,
-                     cudaStream_t st, CliqueShard cs = CliqueShard());
+                     cudaStream_t st, CliqueShard cs = CliqueShard(), CliqueStats* stats_out = nullptr);
 int clique_exact(const uint32_t* bits, int64_t stride32, int n, const int32_t* deg, CliqueScratch s,
                  int32_t* ids_out_host, int64_t* launches, cudaStream_t st, CliqueShard cs = CliqueShard());
 

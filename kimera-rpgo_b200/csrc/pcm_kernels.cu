@@ -702,47 +702,87 @@ void launch_transform_poses(int dim, const double* traj, int entry, int m, const
 }
 
 /* ------------------------------------------------------------------------------------------------
- * mirror: fill row j (columns i < j) from column j of rows i < j, for rows j >= j_begin.
- * One warp transposes a 32x32 bit block with 32 ballots.
+ * mirror: the pairwise kernel writes the strictly-upper triangle (bit (i, j), i < j); this pass fills the lower one
+ * (Pcm.h:756-763 sets both adj(i, j) and adj(j, i)).  HBM-bound bit-matrix transpose: n^2/8 bytes.
+ * One block moves a 512 x 512-bit tile: rows are read as 64-byte segments into shared memory (row pitch 17 words: the 32
+ * rows of a 32x32 block fall into 32 different banks), every 32x32 block is transposed inside a warp with the 5-step
+ * shuffle butterfly and swapped with its mirror block, and the tile is written back as 64-byte row segments.
+ * Diagonal tiles keep their own upper part.  Only tile columns >= j_begin / 512 hold new bits.
  * ---------------------------------------------------------------------------------------------- */
-__global__ void mirror_kernel(uint32_t* bits, int64_t stride32, int n, int wj_begin) {
-  const int lane = threadIdx.x & 31;
-  const int wj = wj_begin + blockIdx.x;                         /* destination rows 32*wj .. +31 */
-  const int wi = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5); /* source rows 32*wi .. +31 */
-  if (wi > wj) return;
-  const int i = wi * 32 + lane;
-  /* source word: row i, columns 32*wj.. ; only the strictly-upper part (col > row) is authoritative */
-  uint32_t src = 0;
-  if (i < n) {
-    src = bits[(size_t)i * stride32 + wj];
-    if (wi == wj) src &= (lane == 31) ? 0u : (0xffffffffu << (lane + 1));
-  }
-  uint32_t mine = 0;
+constexpr int MIRROR_T = 512, MIRROR_W = MIRROR_T / 32, MIRROR_PITCH = MIRROR_W + 1;
+
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
+  /* lane l holds row l; returns column `lane` (bit r = row r's bit `lane`) */
 #pragma unroll
-  for (int b = 0; b < 32; ++b) {
-    const unsigned col = __ballot_sync(0xffffffffu, (src >> b) & 1u); /* column 32*wj+b over rows 32*wi.. */
-    if (lane == b) mine = col;
+  for (int j = 16; j >= 1; j >>= 1) {
+    const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+    x = (lane & j) ? ((x & ~m) | ((y & ~m) >> j)) : ((x & m) | ((y & m) << j));
   }
-  const int j = wj * 32 + lane;
-  if (j < n) {
-    uint32_t* p = bits + (size_t)j * stride32 + wi;
-    if (wi == wj) {
-      /* diagonal block: keep this row's own upper part, set the lower part */
-      const uint32_t upper_mask = (lane == 31) ? 0u : (0xffffffffu << (lane + 1));
-      *p = (*p & upper_mask) | (mine & ~upper_mask & ~(1u << lane));
-    } else {
-      *p = mine;
+  return x;
+}
+
+/* bits of word `w` of row `row` that lie strictly above the diagonal (column > row) */
+__device__ __forceinline__ uint32_t upper_mask(int row, int w) {
+  const int c0 = w * 32;
+  if (c0 > row) return 0xffffffffu;
+  if (c0 + 31 <= row) return 0u;
+  return ~((2u << (row - c0)) - 1u);
+}
+
+__global__ void __launch_bounds__(256) mirror_tile_kernel(uint32_t* bits, int64_t stride32, int n, int tc_begin) {
+  __shared__ uint32_t S[MIRROR_T * MIRROR_PITCH];
+  const int tc = tc_begin + blockIdx.x, tr = blockIdx.y;
+  if (tr > tc) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int half = lane >> 4, wd = lane & 15;
+  const bool diag = tr == tc;
+  /* load the source tile: rows tr*512.., words tc*16.. */
+#pragma unroll 4
+  for (int it = 0; it < MIRROR_T / 16; ++it) {
+    const int r = it * 16 + warp * 2 + half;
+    const int gr = tr * MIRROR_T + r, gw = tc * MIRROR_W + wd;
+    uint32_t v = 0;
+    if (gr < n && gw < stride32 && gw * 32 < n) {
+      v = bits[(size_t)gr * stride32 + gw];
+      if (gw * 32 + 32 > n) v &= (1u << (n - gw * 32)) - 1u;
+      if (diag) v &= upper_mask(gr, gw);
+    }
+    S[r * MIRROR_PITCH + wd] = v;
+  }
+  __syncthreads();
+  /* transpose: block (a, b) <-> block (b, a) */
+  for (int item = warp; item < MIRROR_W * MIRROR_W; item += 8) {
+    const int a = item / MIRROR_W, b = item % MIRROR_W;
+    if (a > b) continue;
+    const uint32_t x = S[(32 * a + lane) * MIRROR_PITCH + b];
+    const uint32_t y = S[(32 * b + lane) * MIRROR_PITCH + a];
+    const uint32_t xt = transpose32(x, lane), yt = transpose32(y, lane);
+    __syncwarp();
+    S[(32 * b + lane) * MIRROR_PITCH + a] = xt;
+    if (a != b) S[(32 * a + lane) * MIRROR_PITCH + b] = yt;
+  }
+  __syncthreads();
+  /* store the mirrored tile: rows tc*512.., words tr*16.. */
+#pragma unroll 4
+  for (int it = 0; it < MIRROR_T / 16; ++it) {
+    const int r = it * 16 + warp * 2 + half;
+    const int gr = tc * MIRROR_T + r, gw = tr * MIRROR_W + wd;
+    if (gr < n && gw < stride32 && gw * 32 < n) {
+      uint32_t* p = bits + (size_t)gr * stride32 + gw;
+      const uint32_t v = S[r * MIRROR_PITCH + wd];
+      if (diag) *p = (*p & upper_mask(gr, gw)) | v;
+      else *p = v;
     }
   }
 }
 
 void launch_mirror(uint32_t* bits, int64_t stride32, int n, int j_begin, cudaStream_t st) {
   if (n < 2 || j_begin >= n) return;
-  const int wj_begin = j_begin / 32;
-  const int wj_end = (n + 31) / 32;
-  const int warps = 4;
-  dim3 grid(wj_end - wj_begin, (wj_end + warps - 1) / warps);
-  mirror_kernel<<<grid, warps * 32, 0, st>>>(bits, stride32, n, wj_begin);
+  const int tiles = (n + MIRROR_T - 1) / MIRROR_T;
+  const int tc_begin = j_begin / MIRROR_T;
+  dim3 grid(tiles - tc_begin, tiles);
+  mirror_tile_kernel<<<grid, 256, 0, st>>>(bits, stride32, n, tc_begin);
 }
 
 /* degree: popcount of each row, one warp per row */

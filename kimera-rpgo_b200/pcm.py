@@ -626,6 +626,12 @@ class PcmGpu:
     def finalize(self, g):
         self._check(self.lib.rpgo_group_finalize(self.h, g), "rpgo_group_finalize")
 
+    def clique_stats(self):
+        """statistics of the last heuristic search (rpgo_clique_stats)"""
+        a, b, e = C.c_int64(), C.c_int64(), C.c_int32()
+        self._check(self.lib.rpgo_clique_stats(self.h, C.byref(a), C.byref(b), C.byref(e)), "rpgo_clique_stats")
+        return dict(row_ands=a.value, chains=b.value, epochs=e.value)
+
     def debug_pass(self, g, which):
         """one bitset pass alone (0 = mirror, 1 = degrees): bandwidth measurements"""
         self._check(self.lib.rpgo_debug_pass(self.h, g, which), "rpgo_debug_pass")
