@@ -81,6 +81,17 @@ def load():
     """dlopen the in-tree CUDA library.  Raises (never falls back) if it is missing."""
     global _lib
     if _lib is None:
+        # measurement builds only (kimera-rpgo_b200/build.py::build_variant): an explicit path to another build of the
+        # same library; still no fallback of any kind
+        path = os.environ.get("RPGO_LIB_PATH", LIB_PATH)
+        if path != LIB_PATH:
+            lib = C.CDLL(path)
+            for name, res, args in SYMBOLS:
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+            return _lib
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 "kimera-rpgo_b200: %s is missing — run `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -22,6 +22,27 @@ def _newest(paths):
     return max(os.path.getmtime(p) for p in paths)
 
 
+def build_variant(tag, extra_flags):
+    """measurement builds (tools/k3_probe.py): the same sources with extra nvcc flags into variants/librpgo_b200_<tag>.so;
+    loaded instead of the product library when RPGO_LIB_PATH points at it"""
+    vdir = os.path.join(HERE, "variants")
+    os.makedirs(os.path.join(vdir, tag), exist_ok=True)
+    out = os.path.join(vdir, "librpgo_b200_%s.so" % tag)
+    objs, procs = [], []
+    for s in SOURCES:
+        o = os.path.join(vdir, tag, s + ".o")
+        objs.append(o)
+        cmd = ["nvcc"] + NVCC_FLAGS + list(extra_flags) + ["-c", os.path.join(CSRC, s), "-o", o]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, p in procs:
+        outp, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(outp)
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    subprocess.check_call(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs + ["-lcudart", "-ldl"])
+    return out
+
+
 def build(force=False, verbose=False):
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]

@@ -358,8 +358,8 @@ static int ensure_group(rpgo_handle* h, Group* g, int64_t need) {
   H_CHECK_CUDA(h, g->pfx.ensure((size_t)ncap, (size_t)g->n, st));
   H_CHECK_CUDA(h, g->deg.ensure((size_t)ncap * 4, 0, st));
   if (g->landmark) H_CHECK_CUDA(h, g->idxa0.ensure((size_t)ncap * 4, (size_t)g->n * 4, st));
-  if (h->loop_check && h->mode == MODE_PCM && !g->landmark) {
-    const size_t rn = (size_t)tiled_record_doubles(h->dim) * 8;
+  if (h->loop_check && !g->landmark) {
+    const size_t rn = (size_t)tiled_record_doubles(h->dim, h->mode) * 8;
     H_CHECK_CUDA(h, g->rec_aos.ensure((size_t)ncap * rn + 256, (size_t)g->n * rn, st));
     H_CHECK_CUDA(h, g->rec_soa.ensure((size_t)ncap * rn + 256, (size_t)((g->n + 31) / 32) * 32 * rn, st));
   }
@@ -411,10 +411,10 @@ static int run_pairwise(rpgo_handle* h, Group* g, int64_t j_begin, double* dist_
   else if (kernel == RPGO_KERNEL_TILED_V1) { variant = 2; kernel = RPGO_KERNEL_TILED; }
   if (dist_dev) kernel = RPGO_KERNEL_DIRECT;
   if (kernel == RPGO_KERNEL_AUTO) kernel = RPGO_KERNEL_TILED;
-  if (kernel == RPGO_KERNEL_TILED && h->mode != MODE_PCM) kernel = RPGO_KERNEL_DIRECT;
+  if (variant != 0 && h->mode != MODE_PCM) variant = 0; /* the cross-check forms exist for the PCM chain only */
   if (kernel == RPGO_KERNEL_TILED) {
     if (g->gathered < g->n) {
-      launch_gather_records(h->dim, v, h->traj.as<double>(), (int)g->gathered, g->rec_aos.as<double>(),
+      launch_gather_records(h->dim, h->mode, v, h->traj.as<double>(), (int)g->gathered, g->rec_aos.as<double>(),
                             g->rec_soa.as<double>(), h->stream);
       g->gathered = g->n;
       h->launches += 1;

@@ -328,9 +328,44 @@ __device__ __forceinline__ void heu_round_body(const uint32_t* __restrict__ bits
             }
           }
         }
+      } else if (t <= HEU_PRE * TH) {
+        /* many picks in this window: AND all of their rows into every surviving word, four picks at a time.  All row words
+         * of a group (4 picks x up to HEU_PRE words of this thread) are requested before any is used: one memory round trip
+         * per group of picks instead of one per word */
+        uint32_t r[HEU_PRE];
+#pragma unroll
+        for (int k = 0; k < HEU_PRE; ++k) {
+          const int w = tid + k * TH;
+          r[k] = w < t ? R[w] : 0u;
+        }
+        uint32_t q = P;
+        while (q) {
+          int b4[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            b4[c] = q ? 31 - __clz(q) : -1;
+            if (b4[c] >= 0) q &= ~(1u << b4[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int k = 0; k < HEU_PRE; ++k)
+              pre[c][k] = (b4[c] >= 0 && r[k]) ? bits[(size_t)(t * 32 + b4[c]) * stride32 + tid + k * TH] : 0xffffffffu;
+          }
+#pragma unroll
+          for (int k = 0; k < HEU_PRE; ++k) r[k] &= (pre[0][k] & pre[1][k]) & (pre[2][k] & pre[3][k]);
+        }
+#pragma unroll
+        for (int k = 0; k < HEU_PRE; ++k) {
+          const int w = tid + k * TH;
+          if (w < t) {
+            R[w] = r[k];
+            cnt += __popc(r[k]);
+            if (r[k]) top = w;
+          }
+        }
       } else {
-        /* many picks in this window: AND all of their rows into every surviving word.  The row loads of one word do
-         * not depend on each other (no early exit), four are kept in flight per thread */
+        /* rows wider than the register window (n > HEU_PRE * TH * 32): word by word, four picks in flight */
         for (int w = tid; w < t; w += blockDim.x) {
           uint32_t r = R[w];
           if (r) {

@@ -74,8 +74,8 @@ void launch_scatter_entries(int dim, int n, const double* entries, const uint64_
 /* K3 */
 void launch_pairwise_direct(int dim, int mode, GroupView g, const double* traj, int j_begin, Shard sh, Thresholds th,
                             Flagged fl, double* dist_out, cudaStream_t st);
-int tiled_record_doubles(int dim);
-void launch_gather_records(int dim, GroupView g, const double* traj, int k0, double* aos, double* soa, cudaStream_t st);
+int tiled_record_doubles(int dim, int mode);
+void launch_gather_records(int dim, int mode, GroupView g, const double* traj, int k0, double* aos, double* soa, cudaStream_t st);
 /* variant: 0 = default (phase-shifted warp groups, straight-line pair function); the two cross-check forms
  * RPGO_KERNEL_TILED_ONE_GROUP / RPGO_KERNEL_TILED_V1 select 1 / 2 */
 void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, const double* soa, int j_begin, Shard sh,

@@ -711,16 +711,36 @@ void launch_transform_poses(int dim, const double* traj, int entry, int m, const
  * ---------------------------------------------------------------------------------------------- */
 constexpr int MIRROR_T = 512, MIRROR_W = MIRROR_T / 32, MIRROR_PITCH = MIRROR_W + 1;
 
-__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
-  /* lane l holds row l; returns column `lane` (bit r = row r's bit `lane`) */
-#pragma unroll
-  for (int j = 16; j >= 1; j >>= 1) {
-    const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
-    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
-    x = (lane & j) ? ((x & ~m) | ((y & ~m) >> j)) : ((x & m) | ((y & m) << j));
+/* 32x32 bit transpose inside a warp: lane l holds row l, the result in lane c is column c (bit r = row r's bit c).
+ * Five exchange steps with the partner lane l ^ j (j = 16, 8, 4, 2, 1); each step keeps one half of the own word and takes
+ * the other half from the partner, moved by j bits.  The two coarse steps are byte permutations (one PRMT), the fine ones a
+ * rotate plus one three-input logic op; the per-lane constants live in Tr32 (computed once per thread). */
+struct Tr32 {
+  uint32_t sel16, sel8;      /* PRMT selectors of the 16- and 8-bit steps */
+  uint32_t keep4, keep2, keep1; /* bits kept from the own word in the 4 / 2 / 1-bit steps */
+  uint32_t rot4, rot2, rot1; /* left-rotation of the partner's word */
+  __device__ __forceinline__ explicit Tr32(int lane) {
+    sel16 = (lane & 16) ? 0x3276u : 0x5410u;
+    sel8 = (lane & 8) ? 0x3715u : 0x6240u;
+    keep4 = (lane & 4) ? 0xF0F0F0F0u : 0x0F0F0F0Fu;
+    keep2 = (lane & 2) ? 0xCCCCCCCCu : 0x33333333u;
+    keep1 = (lane & 1) ? 0xAAAAAAAAu : 0x55555555u;
+    rot4 = (lane & 4) ? 28u : 4u;
+    rot2 = (lane & 2) ? 30u : 2u;
+    rot1 = (lane & 1) ? 31u : 1u;
   }
-  return x;
-}
+  __device__ __forceinline__ uint32_t operator()(uint32_t x) const {
+    x = __byte_perm(x, __shfl_xor_sync(0xffffffffu, x, 16), sel16);
+    x = __byte_perm(x, __shfl_xor_sync(0xffffffffu, x, 8), sel8);
+    uint32_t y = __shfl_xor_sync(0xffffffffu, x, 4);
+    x = (x & keep4) | (__funnelshift_l(y, y, rot4) & ~keep4);
+    y = __shfl_xor_sync(0xffffffffu, x, 2);
+    x = (x & keep2) | (__funnelshift_l(y, y, rot2) & ~keep2);
+    y = __shfl_xor_sync(0xffffffffu, x, 1);
+    x = (x & keep1) | (__funnelshift_l(y, y, rot1) & ~keep1);
+    return x;
+  }
+};
 
 /* bits of word `w` of row `row` that lie strictly above the diagonal (column > row) */
 __device__ __forceinline__ uint32_t upper_mask(int row, int w) {
@@ -730,49 +750,82 @@ __device__ __forceinline__ uint32_t upper_mask(int row, int w) {
   return ~((2u << (row - c0)) - 1u);
 }
 
-__global__ void __launch_bounds__(256) mirror_tile_kernel(uint32_t* bits, int64_t stride32, int n, int tc_begin) {
+constexpr int MIRROR_PATCH = 16; /* concurrently resident blocks cover compact 16 x 16-tile patches: neighbouring tiles touch
+                                    neighbouring 64-byte pieces of the same DRAM pages at about the same time, on the read side
+                                    (same rows, adjacent columns) and on the write side (same mirrored rows) alike */
+
+__global__ void __launch_bounds__(256) mirror_tile_kernel(uint32_t* bits, int64_t stride32, int n, int tc_begin, int tiles,
+                                                          int patches_x) {
   __shared__ uint32_t S[MIRROR_T * MIRROR_PITCH];
-  const int tc = tc_begin + blockIdx.x, tr = blockIdx.y;
-  if (tr > tc) return;
+  const int patch = blockIdx.x / (MIRROR_PATCH * MIRROR_PATCH), inner = blockIdx.x % (MIRROR_PATCH * MIRROR_PATCH);
+  const int tc = tc_begin + (patch % patches_x) * MIRROR_PATCH + inner % MIRROR_PATCH;
+  const int tr = (patch / patches_x) * MIRROR_PATCH + inner / MIRROR_PATCH;
+  if (tc >= tiles || tr > tc) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int half = lane >> 4, wd = lane & 15;
+  const int rsub = lane >> 2, q4 = (lane & 3) * 4; /* a warp moves 8 rows x 64 bytes per instruction, 16 bytes per lane */
   const bool diag = tr == tc;
-  /* load the source tile: rows tr*512.., words tc*16.. */
-#pragma unroll 4
-  for (int it = 0; it < MIRROR_T / 16; ++it) {
-    const int r = it * 16 + warp * 2 + half;
-    const int gr = tr * MIRROR_T + r, gw = tc * MIRROR_W + wd;
-    uint32_t v = 0;
-    if (gr < n && gw < stride32 && gw * 32 < n) {
-      v = bits[(size_t)gr * stride32 + gw];
-      if (gw * 32 + 32 > n) v &= (1u << (n - gw * 32)) - 1u;
-      if (diag) v &= upper_mask(gr, gw);
+  const bool edge = diag || (tc + 1) * MIRROR_T > n;
+  /* load the source tile: rows tr*512.., words tc*16.. (all eight 16-byte loads of a thread are in flight together) */
+  {
+    uint4 v[MIRROR_T / 64];
+#pragma unroll
+    for (int it = 0; it < MIRROR_T / 64; ++it) {
+      const int gr = tr * MIRROR_T + it * 64 + warp * 8 + rsub, gw = tc * MIRROR_W + q4;
+      v[it] = make_uint4(0u, 0u, 0u, 0u);
+      if (gr < n && gw < stride32 && gw * 32 < n) v[it] = *reinterpret_cast<const uint4*>(bits + (size_t)gr * stride32 + gw);
     }
-    S[r * MIRROR_PITCH + wd] = v;
+#pragma unroll
+    for (int it = 0; it < MIRROR_T / 64; ++it) {
+      const int r = it * 64 + warp * 8 + rsub;
+      const int gr = tr * MIRROR_T + r, gw = tc * MIRROR_W + q4;
+      uint32_t x[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+      if (edge) { /* tiles on the diagonal or at the right border: mask what is not strictly-upper / beyond column n */
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c0 = (gw + k) * 32;
+          if (c0 >= n) x[k] = 0u;
+          else if (c0 + 32 > n) x[k] &= (1u << (n - c0)) - 1u;
+          if (diag) x[k] &= upper_mask(gr, gw + k);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) S[r * MIRROR_PITCH + q4 + k] = x[k];
+    }
   }
   __syncthreads();
-  /* transpose: block (a, b) <-> block (b, a) */
-  for (int item = warp; item < MIRROR_W * MIRROR_W; item += 8) {
-    const int a = item / MIRROR_W, b = item % MIRROR_W;
-    if (a > b) continue;
-    const uint32_t x = S[(32 * a + lane) * MIRROR_PITCH + b];
-    const uint32_t y = S[(32 * b + lane) * MIRROR_PITCH + a];
-    const uint32_t xt = transpose32(x, lane), yt = transpose32(y, lane);
-    __syncwarp();
-    S[(32 * b + lane) * MIRROR_PITCH + a] = xt;
-    if (a != b) S[(32 * a + lane) * MIRROR_PITCH + b] = yt;
+  /* transpose: block (a, b) <-> block (b, a); the 136 pairs a <= b are spread evenly over the warps */
+  {
+    const Tr32 tr32(lane);
+    for (int item = warp; item < MIRROR_W * (MIRROR_W + 1) / 2; item += 8) {
+      int b = (int)((sqrtf(8.0f * (float)item + 1.0f) - 1.0f) * 0.5f); /* triangular root; exact for item < 2^20 after the fix-up */
+      b += ((b + 1) * (b + 2) / 2 <= item) ? 1 : 0;
+      b -= (b * (b + 1) / 2 > item) ? 1 : 0;
+      const int a = item - b * (b + 1) / 2;
+      const uint32_t x = S[(32 * a + lane) * MIRROR_PITCH + b];
+      const uint32_t y = S[(32 * b + lane) * MIRROR_PITCH + a];
+      const uint32_t xt = tr32(x), yt = tr32(y);
+      __syncwarp();
+      S[(32 * b + lane) * MIRROR_PITCH + a] = xt;
+      if (a != b) S[(32 * a + lane) * MIRROR_PITCH + b] = yt;
+    }
   }
   __syncthreads();
   /* store the mirrored tile: rows tc*512.., words tr*16.. */
-#pragma unroll 4
-  for (int it = 0; it < MIRROR_T / 16; ++it) {
-    const int r = it * 16 + warp * 2 + half;
-    const int gr = tc * MIRROR_T + r, gw = tr * MIRROR_W + wd;
+#pragma unroll
+  for (int it = 0; it < MIRROR_T / 64; ++it) {
+    const int r = it * 64 + warp * 8 + rsub;
+    const int gr = tc * MIRROR_T + r, gw = tr * MIRROR_W + q4;
     if (gr < n && gw < stride32 && gw * 32 < n) {
-      uint32_t* p = bits + (size_t)gr * stride32 + gw;
-      const uint32_t v = S[r * MIRROR_PITCH + wd];
-      if (diag) *p = (*p & upper_mask(gr, gw)) | v;
-      else *p = v;
+      uint4* p = reinterpret_cast<uint4*>(bits + (size_t)gr * stride32 + gw);
+      uint4 v = make_uint4(S[r * MIRROR_PITCH + q4], S[r * MIRROR_PITCH + q4 + 1], S[r * MIRROR_PITCH + q4 + 2], S[r * MIRROR_PITCH + q4 + 3]);
+      if (diag) { /* keep this row's own upper part */
+        const uint4 o = *p;
+        v.x |= o.x & upper_mask(gr, gw);
+        v.y |= o.y & upper_mask(gr, gw + 1);
+        v.z |= o.z & upper_mask(gr, gw + 2);
+        v.w |= o.w & upper_mask(gr, gw + 3);
+      }
+      *p = v;
     }
   }
 }
@@ -781,8 +834,8 @@ void launch_mirror(uint32_t* bits, int64_t stride32, int n, int j_begin, cudaStr
   if (n < 2 || j_begin >= n) return;
   const int tiles = (n + MIRROR_T - 1) / MIRROR_T;
   const int tc_begin = j_begin / MIRROR_T;
-  dim3 grid(tiles - tc_begin, tiles);
-  mirror_tile_kernel<<<grid, 256, 0, st>>>(bits, stride32, n, tc_begin);
+  const int patches_x = (tiles - tc_begin + MIRROR_PATCH - 1) / MIRROR_PATCH, patches_y = (tiles + MIRROR_PATCH - 1) / MIRROR_PATCH;
+  mirror_tile_kernel<<<patches_x * patches_y * MIRROR_PATCH * MIRROR_PATCH, 256, 0, st>>>(bits, stride32, n, tc_begin, tiles, patches_x);
 }
 
 /* degree: popcount of each row, one warp per row */

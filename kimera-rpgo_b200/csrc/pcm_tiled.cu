@@ -29,27 +29,41 @@
 
 namespace rpgo {
 
-template <int D>
+/* PCM records carry full entries (pose, covariance, flags); PcmSimple needs poses and hop counts only, so its records
+ * are compact (pose, rotation_info, node: rpgo_pair_v2.cuh::SimpleEntry) — 3.5x less shared memory and L2 traffic */
+template <int D, int MODE = MODE_PCM>
 struct Rec {
-  static constexpr int E = Dim<D>::ENTRY;
+  static constexpr int E = MODE == MODE_PCM ? Dim<D>::ENTRY : SimpleEntry<D>::E;
   static constexpr int N = 3 * E + 2; /* doubles per record (16-byte multiple) */
   static constexpr int OFF_TF = 0, OFF_TB = E, OFF_LC = 2 * E, OFF_PFX = 3 * E;
+  static constexpr int SCR = MODE == MODE_PCM ? Dim<D>::ENTRY : 0; /* per-thread scratch doubles (b_odom_d of the PCM chain) */
 };
+static_assert(Rec<3, MODE_SIMPLE>::N % 2 == 0 && Rec<2, MODE_SIMPLE>::N % 2 == 0 && Rec<3>::N % 2 == 0 && Rec<2>::N % 2 == 0,
+              "bulk copies move 16-byte units");
 
-int tiled_record_doubles(int dim) { return dim == 3 ? Rec<3>::N : Rec<2>::N; }
+int tiled_record_doubles(int dim, int mode) {
+  if (mode == MODE_PCM) return dim == 3 ? Rec<3>::N : Rec<2>::N;
+  return dim == 3 ? Rec<3, MODE_SIMPLE>::N : Rec<2, MODE_SIMPLE>::N;
+}
 
 /* ---- gather -------------------------------------------------------------------------------------- */
-template <int D>
+template <int D, int MODE>
 __global__ void gather_records_kernel(GroupView g, const double* __restrict__ traj, int k0, double* aos, double* soa) {
-  constexpr int E = Rec<D>::E, RN = Rec<D>::N;
+  constexpr int E = Rec<D, MODE>::E, RN = Rec<D, MODE>::N, TE = Dim<D>::ENTRY;
   const int k = k0 + blockIdx.x;
   if (k >= g.n) return;
   for (int f = threadIdx.x; f < RN; f += blockDim.x) {
     double v = 0.0;
-    if (f < E) v = traj[(size_t)g.idx_front[k] * E + f];
-    else if (f < 2 * E) v = traj[(size_t)g.idx_back[k] * E + (f - E)];
-    else if (f < 3 * E) v = g.lc[(size_t)k * E + (f - 2 * E)];
-    else if (f == 3 * E) v = (double)g.pfx_front[k];
+    if (f < 3 * E) {
+      const int which = f / E, e = f - which * E;
+      /* source entry (trajectory / closure tables keep full entries) and field inside it */
+      const double* src = which == 0 ? traj + (size_t)g.idx_front[k] * TE : which == 1 ? traj + (size_t)g.idx_back[k] * TE : g.lc + (size_t)k * TE;
+      int sf = e;
+      if (MODE != MODE_PCM) sf = e < Dim<D>::PS ? e : (e == SimpleEntry<D>::OFF_ROT ? Dim<D>::OFF_ROT : Dim<D>::OFF_NODE);
+      v = src[sf];
+    } else if (f == 3 * E) {
+      v = (double)g.pfx_front[k];
+    }
     aos[(size_t)k * RN + f] = v;
     soa[((size_t)(k >> 5) * RN + f) * 32 + (k & 31)] = v;
   }
@@ -88,24 +102,48 @@ __device__ __forceinline__ bool row_owned_t(const Shard& sh, int i) {
   return c == sh.rank || c == 2 * (int64_t)sh.world - 1 - sh.rank;
 }
 
-/* exact general path for the rare lanes the straight-line code flags (kept out of line: cold code) */
+/* exact general paths for the rare lanes the straight-line code flags (kept out of line: cold code) */
 template <int D>
 __device__ __noinline__ bool pair_check_exact(const double* Ta, int sa, const double* Tb, int sb, const double* lci, int sli,
                                               const double* Tc, int sc, const double* Td, int sd, const double* lcj, int slj,
                                               double* scr, int ss, const Thresholds* th, double* dist, bool* near) {
   return pair_check_v1<D>(Ta, sa, Tb, sb, lci, sli, Tc, sc, Td, sd, lcj, slj, scr, ss, *th, dist, near);
 }
+template <int D>
+__device__ __noinline__ bool pair_simple_exact(const double* Ta, int sa, const double* Tb, int sb, const double* lci, int sli,
+                                               const double* Tc, int sc, const double* Td, int sd, const double* lcj, int slj,
+                                               const Thresholds* th, double* dist, bool* near) {
+  return pair_check_simple_exact<D>(Ta, sa, Tb, sb, lci, sli, Tc, sc, Td, sd, lcj, slj, *th, dist, near);
+}
+
+/* one pair through the mode's straight-line function; flagged lanes go through the exact general code */
+template <int D, int MODE>
+__device__ __forceinline__ bool tile_pair(const double* Ta, int sa, const double* Tb, int sb, const double* lci, int sli,
+                                          const double* Tc, int sc, const double* Td, int sd, const double* lcj, int slj,
+                                          double* scr, int ss, const Thresholds& th, bool* near) {
+  double dist;
+  bool bad, ok;
+  if (MODE == MODE_PCM) {
+    ok = pair_check_v2<D>(Ta, sa, Tb, sb, lci, sli, Tc, sc, Td, sd, lcj, slj, scr, ss, th, &dist, near, &bad);
+    if (bad) ok = pair_check_exact<D>(Ta, sa, Tb, sb, lci, sli, Tc, sc, Td, sd, lcj, slj, scr, ss, &th, &dist, near);
+  } else {
+    ok = pair_check_simple_v2<D>(Ta, sa, Tb, sb, lci, sli, Tc, sc, Td, sd, lcj, slj, th, &dist, near, &bad);
+    if (bad) ok = pair_simple_exact<D>(Ta, sa, Tb, sb, lci, sli, Tc, sc, Td, sd, lcj, slj, &th, &dist, near);
+  }
+  return ok;
+}
 
 constexpr int TILE_SEG = 512;   /* rows per work item */
 
-template <int D, int TILE_WARPS>
+template <int D, int TILE_WARPS, int MODE = MODE_PCM>
 struct TiledSmem {
-  static constexpr int RN = Rec<D>::N, E = Rec<D>::E;
+  static constexpr int RN = Rec<D, MODE>::N;
   static constexpr size_t JT = (size_t)RN * 32 * 8;                 /* column slab */
   static constexpr size_t IT = (size_t)2 * TILE_WARPS * RN * 8;     /* 2 stages of row records */
-  static constexpr size_t SCR = (size_t)E * TILE_WARPS * 32 * 8;    /* per-thread scratch entry */
+  static constexpr size_t SCR = (size_t)Rec<D, MODE>::SCR * TILE_WARPS * 32 * 8; /* per-thread scratch entry */
   static constexpr size_t BYTES = JT + IT + SCR + 256;
 };
+
 
 template <int D, int TILE_WARPS, int MINB, int PAIRFN>
 __global__ void __launch_bounds__(TILE_WARPS * 32, MINB)
@@ -218,19 +256,24 @@ __device__ __forceinline__ void group_of(int w, int& grp, int& wi) {
   else { grp = w % G; wi = w / G; }
 }
 
-template <int D, int TILE_WARPS, int G, int SEG>
-__global__ void __launch_bounds__(TILE_WARPS * 32, 1)
+#ifndef RPGO_K3_LB_THREADS /* measurement builds: declare a larger block than is launched = a lower register cap */
+#define RPGO_K3_LB_THREADS(tw) ((tw) * 32)
+#endif
+template <int D, int MODE, int TILE_WARPS, int G, int SEG, int MINB>
+__global__ void __launch_bounds__(RPGO_K3_LB_THREADS(TILE_WARPS), MINB)
     pairwise_grouped_kernel(GroupView g, const double* __restrict__ aos, const double* __restrict__ soa, int j_begin,
                             int cb_begin, Shard sh, Thresholds th, Flagged fl) {
-  constexpr int RN = Rec<D>::N;
+  typedef Rec<D, MODE> R;
+  typedef TiledSmem<D, TILE_WARPS, MODE> SM;
+  constexpr int RN = R::N;
   constexpr int WG = TILE_WARPS / G;
   static_assert(WG * G == TILE_WARPS, "groups must divide the block");
   static_assert(1 + 2 * G <= 32, "mbarrier slots");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* Jt = reinterpret_cast<double*>(smem_raw);
-  double* It = reinterpret_cast<double*>(smem_raw + TiledSmem<D, TILE_WARPS>::JT);
-  double* Scr = reinterpret_cast<double*>(smem_raw + TiledSmem<D, TILE_WARPS>::JT + TiledSmem<D, TILE_WARPS>::IT);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TiledSmem<D, TILE_WARPS>::JT + TiledSmem<D, TILE_WARPS>::IT + TiledSmem<D, TILE_WARPS>::SCR);
+  double* It = reinterpret_cast<double*>(smem_raw + SM::JT);
+  double* Scr = reinterpret_cast<double*>(smem_raw + SM::JT + SM::IT);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + SM::JT + SM::IT + SM::SCR);
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   int grp, wi;
@@ -251,8 +294,8 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 1)
   }
   __syncthreads();
   if (tid == 0) {
-    mbar_expect_tx(&bars[0], (uint32_t)TiledSmem<D, TILE_WARPS>::JT);
-    tma_load_1d(Jt, soa + (size_t)cb * RN * 32, (uint32_t)TiledSmem<D, TILE_WARPS>::JT, &bars[0]);
+    mbar_expect_tx(&bars[0], (uint32_t)SM::JT);
+    tma_load_1d(Jt, soa + (size_t)cb * RN * 32, (uint32_t)SM::JT, &bars[0]);
   }
   const bool leader = (wi == 0 && lane == 0);
   double* Ig = It + (size_t)grp * 2 * WG * RN;       /* this group's two stages */
@@ -267,7 +310,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 1)
 
   const int j = cb * 32 + lane;
   const double* Jl = Jt + lane;
-  const uint8_t pc = (uint8_t)Jl[Rec<D>::OFF_PFX * 32];
+  const uint8_t pc = (uint8_t)Jl[R::OFF_PFX * 32];
   double* scr = Scr + tid;
 
   int it = 0;
@@ -285,16 +328,24 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 1)
       const double* Ir = Ig + ((size_t)stage * WG + wi) * RN;
       bool ok = false;
       if (j < g.n && j > i && j >= j_begin) {
-        const uint8_t pa = (uint8_t)Ir[Rec<D>::OFF_PFX];
-        const double* Tc = (pa != pc) ? Jl + Rec<D>::OFF_TB * 32 : Jl + Rec<D>::OFF_TF * 32;
-        const double* Td = (pa != pc) ? Jl + Rec<D>::OFF_TF * 32 : Jl + Rec<D>::OFF_TB * 32;
-        double dist;
-        bool near, bad;
-        ok = pair_check_v2<D>(Ir + Rec<D>::OFF_TF, 1, Ir + Rec<D>::OFF_TB, 1, Ir + Rec<D>::OFF_LC, 1, Tc, 32, Td, 32,
-                              Jl + Rec<D>::OFF_LC * 32, 32, scr, TILE_WARPS * 32, th, &dist, &near, &bad);
-        if (bad)
-          ok = pair_check_exact<D>(Ir + Rec<D>::OFF_TF, 1, Ir + Rec<D>::OFF_TB, 1, Ir + Rec<D>::OFF_LC, 1, Tc, 32, Td, 32,
-                                   Jl + Rec<D>::OFF_LC * 32, 32, scr, TILE_WARPS * 32, &th, &dist, &near);
+        const uint8_t pa = (uint8_t)Ir[R::OFF_PFX];
+        /* Pcm.h:691-698: if the prefixes of a and c differ, c and d swap (measurement not inverted) */
+        const double* Tc = (pa != pc) ? Jl + R::OFF_TB * 32 : Jl + R::OFF_TF * 32;
+        const double* Td = (pa != pc) ? Jl + R::OFF_TF * 32 : Jl + R::OFF_TB * 32;
+        bool near;
+        /* the 6x6 chain is called directly: through the tile_pair wrapper ptxas spills 8 more bytes per thread and the 3D
+         * kernel loses 2 % (measured, profiles/r2_k3_variants.md) */
+        if constexpr (MODE == MODE_PCM) {
+          double dist;
+          bool bad;
+          ok = pair_check_v2<D>(Ir + R::OFF_TF, 1, Ir + R::OFF_TB, 1, Ir + R::OFF_LC, 1, Tc, 32, Td, 32,
+                                Jl + R::OFF_LC * 32, 32, scr, TILE_WARPS * 32, th, &dist, &near, &bad);
+          if (bad)
+            ok = pair_check_exact<D>(Ir + R::OFF_TF, 1, Ir + R::OFF_TB, 1, Ir + R::OFF_LC, 1, Tc, 32, Td, 32,
+                                     Jl + R::OFF_LC * 32, 32, scr, TILE_WARPS * 32, &th, &dist, &near);
+        } else
+          ok = tile_pair<D, MODE>(Ir + R::OFF_TF, 1, Ir + R::OFF_TB, 1, Ir + R::OFF_LC, 1, Tc, 32, Td, 32, Jl + R::OFF_LC * 32, 32, scr,
+                                TILE_WARPS * 32, th, &near);
         if (near) {
           const unsigned long long slot = atomicAdd(fl.count, 1ULL);
           if ((int64_t)slot < fl.cap) {
@@ -324,11 +375,12 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 1)
  * array-of-structs record, staged in shared memory once per block).  Same pair function, same argument roles (i older,
  * j newer), so the decisions are identical; bit (i, j) is set with atomicOr because a row word may receive several new
  * columns from different blocks. */
-template <int D, int TILE_WARPS>
+template <int D, int MODE, int TILE_WARPS>
 __global__ void __launch_bounds__(TILE_WARPS * 32, 1)
     pairwise_column_kernel(GroupView g, const double* __restrict__ aos, const double* __restrict__ soa, int j_begin, Shard sh,
                            Thresholds th, Flagged fl) {
-  constexpr int RN = Rec<D>::N, E = Rec<D>::E;
+  typedef Rec<D, MODE> R;
+  constexpr int RN = R::N;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* Jrec = reinterpret_cast<double*>(smem_raw);                 /* the new closure's record (RN doubles) */
   double* Scr = reinterpret_cast<double*>(smem_raw + ((RN * 8 + 127) / 128) * 128);
@@ -340,22 +392,17 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 1)
   const int rs = blockIdx.x * TILE_WARPS + w; /* row slab of this warp */
   const int i = rs * 32 + lane;
   if (rs * 32 >= j) return;                   /* whole slab at or beyond the column: nothing below the diagonal here */
-  bool ok = false;
   if (i < j && i < g.n && row_owned_t(sh, i)) {
     const double* Il = soa + (size_t)rs * RN * 32 + lane; /* field f of closure i: Il[f * 32] */
-    const uint8_t pa = (uint8_t)Il[Rec<D>::OFF_PFX * 32];
-    const uint8_t pc = (uint8_t)Jrec[Rec<D>::OFF_PFX];
+    const uint8_t pa = (uint8_t)Il[R::OFF_PFX * 32];
+    const uint8_t pc = (uint8_t)Jrec[R::OFF_PFX];
     /* Pcm.h:691-698: if the prefixes of a and c differ, c and d swap (measurement not inverted) */
-    const double* Tc = (pa != pc) ? Jrec + Rec<D>::OFF_TB : Jrec + Rec<D>::OFF_TF;
-    const double* Td = (pa != pc) ? Jrec + Rec<D>::OFF_TF : Jrec + Rec<D>::OFF_TB;
+    const double* Tc = (pa != pc) ? Jrec + R::OFF_TB : Jrec + R::OFF_TF;
+    const double* Td = (pa != pc) ? Jrec + R::OFF_TF : Jrec + R::OFF_TB;
     double* scr = Scr + tid;
-    double dist;
-    bool near, bad;
-    ok = pair_check_v2<D>(Il + Rec<D>::OFF_TF * 32, 32, Il + Rec<D>::OFF_TB * 32, 32, Il + Rec<D>::OFF_LC * 32, 32, Tc, 1, Td, 1,
-                          Jrec + Rec<D>::OFF_LC, 1, scr, TILE_WARPS * 32, th, &dist, &near, &bad);
-    if (bad)
-      ok = pair_check_exact<D>(Il + Rec<D>::OFF_TF * 32, 32, Il + Rec<D>::OFF_TB * 32, 32, Il + Rec<D>::OFF_LC * 32, 32, Tc, 1, Td, 1,
-                               Jrec + Rec<D>::OFF_LC, 1, scr, TILE_WARPS * 32, &th, &dist, &near);
+    bool near;
+    const bool ok = tile_pair<D, MODE>(Il + R::OFF_TF * 32, 32, Il + R::OFF_TB * 32, 32, Il + R::OFF_LC * 32, 32, Tc, 1, Td, 1,
+                                       Jrec + R::OFF_LC, 1, scr, TILE_WARPS * 32, th, &near);
     if (near) {
       const unsigned long long slot = atomicAdd(fl.count, 1ULL);
       if ((int64_t)slot < fl.cap) {
@@ -367,29 +414,29 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 1)
     if (ok) atomicOr(g.bits + (size_t)i * g.stride32 + (j >> 5), 1u << (j & 31));
     else atomicAnd(g.bits + (size_t)i * g.stride32 + (j >> 5), ~(1u << (j & 31)));
   }
-  (void)E;
 }
 
-template <int D>
+template <int D, int MODE>
 static void launch_column(GroupView g, const double* aos, const double* soa, int j_begin, Shard sh, Thresholds th, Flagged fl,
                           cudaStream_t st) {
   constexpr int TW = 12;
-  const size_t smem = ((Rec<D>::N * 8 + 127) / 128) * 128 + (size_t)Rec<D>::E * TW * 32 * 8;
+  const size_t smem = ((Rec<D, MODE>::N * 8 + 127) / 128) * 128 + (size_t)Rec<D, MODE>::SCR * TW * 32 * 8;
   static PerDeviceOnce once;
-  if (once.first()) cudaFuncSetAttribute(pairwise_column_kernel<D, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (once.first()) cudaFuncSetAttribute(pairwise_column_kernel<D, MODE, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int slabs = (g.n + 31) / 32;
   dim3 grid((slabs + TW - 1) / TW, g.n - j_begin);
-  pairwise_column_kernel<D, TW><<<grid, TW * 32, smem, st>>>(g, aos, soa, j_begin, sh, th, fl);
+  pairwise_column_kernel<D, MODE, TW><<<grid, TW * 32, smem, st>>>(g, aos, soa, j_begin, sh, th, fl);
 }
 
-static void gather_launch(int dim, GroupView g, const double* traj, int k0, double* aos, double* soa, cudaStream_t st) {
+void launch_gather_records(int dim, int mode, GroupView g, const double* traj, int k0, double* aos, double* soa, cudaStream_t st) {
   if (k0 >= g.n) return;
-  if (dim == 3) gather_records_kernel<3><<<g.n - k0, 160, 0, st>>>(g, traj, k0, aos, soa);
-  else gather_records_kernel<2><<<g.n - k0, 64, 0, st>>>(g, traj, k0, aos, soa);
-}
-
-void launch_gather_records(int dim, GroupView g, const double* traj, int k0, double* aos, double* soa, cudaStream_t st) {
-  gather_launch(dim, g, traj, k0, aos, soa, st);
+  if (mode == MODE_PCM) {
+    if (dim == 3) gather_records_kernel<3, MODE_PCM><<<g.n - k0, 160, 0, st>>>(g, traj, k0, aos, soa);
+    else gather_records_kernel<2, MODE_PCM><<<g.n - k0, 64, 0, st>>>(g, traj, k0, aos, soa);
+  } else {
+    if (dim == 3) gather_records_kernel<3, MODE_SIMPLE><<<g.n - k0, 64, 0, st>>>(g, traj, k0, aos, soa);
+    else gather_records_kernel<2, MODE_SIMPLE><<<g.n - k0, 32, 0, st>>>(g, traj, k0, aos, soa);
+  }
 }
 
 /* ---- validation of the straight-line operations against the built-in IEEE ones (debug hook) -------------- */
@@ -454,26 +501,79 @@ static void launch_variant(GroupView g, const double* aos, const double* soa, in
   pairwise_tiled_kernel<D, TW, MINB, PAIRFN><<<grid, TW * 32, TiledSmem<D, TW>::BYTES, st>>>(g, aos, soa, j_begin, cb_begin, sh, th, fl);
 }
 
-template <int D, int TW, int G, int SEG>
+template <int D, int MODE, int TW, int G, int SEG, int MINB>
 static void launch_grouped(GroupView g, const double* aos, const double* soa, int j_begin, int cb_begin, int cb_end, Shard sh,
                            Thresholds th, Flagged fl, cudaStream_t st) {
   static PerDeviceOnce once;
-  if (once.first())
-    cudaFuncSetAttribute(pairwise_grouped_kernel<D, TW, G, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)TiledSmem<D, TW>::BYTES);
+  if (once.first()) {
+    cudaFuncSetAttribute(pairwise_grouped_kernel<D, MODE, TW, G, SEG, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)TiledSmem<D, TW, MODE>::BYTES);
+    /* MINB blocks per SM only materialise if the shared-memory carve-out is large enough for all of them */
+    cudaFuncSetAttribute(pairwise_grouped_kernel<D, MODE, TW, G, SEG, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+  }
   dim3 grid((g.n + SEG - 1) / SEG, cb_end - cb_begin);
-  pairwise_grouped_kernel<D, TW, G, SEG><<<grid, TW * 32, TiledSmem<D, TW>::BYTES, st>>>(g, aos, soa, j_begin, cb_begin, sh, th, fl);
+  pairwise_grouped_kernel<D, MODE, TW, G, SEG, MINB><<<grid, TW * 32, TiledSmem<D, TW, MODE>::BYTES, st>>>(g, aos, soa, j_begin, cb_begin,
+                                                                                                       sh, th, fl);
+}
+
+/* Block shapes per pair function (measured, profiles/r2_*): the 6x6 chain needs 168 registers and 50 doubles of scratch per
+ * thread, so one 12-warp block fills an SM; the 3x3 chain and the pose-only PcmSimple chains are small enough for 2-3
+ * blocks of 8 warps per SM, which is what hides their dependency latency. */
+#ifndef RPGO_2D_MINB
+#define RPGO_2D_MINB 3
+#endif
+#ifndef RPGO_S3_MINB
+#define RPGO_S3_MINB 3
+#endif
+#ifndef RPGO_S2_MINB
+#define RPGO_S2_MINB 3
+#endif
+template <int D, int MODE>
+struct TileShape;
+template <> struct TileShape<3, MODE_PCM> { static constexpr int TW = 12, G = 3, SEG = 504, SEG_SMALL = 48, MINB = 1; };
+#ifndef RPGO_2D_TW
+#define RPGO_2D_TW 8
+#define RPGO_2D_G 2
+#define RPGO_2D_SEG 512
+#endif
+#ifndef RPGO_S3_TW
+#define RPGO_S3_TW 8
+#define RPGO_S3_G 2
+#define RPGO_S3_SEG 512
+#endif
+template <> struct TileShape<2, MODE_PCM> { static constexpr int TW = RPGO_2D_TW, G = RPGO_2D_G, SEG = RPGO_2D_SEG, SEG_SMALL = 64, MINB = RPGO_2D_MINB; };
+template <> struct TileShape<3, MODE_SIMPLE> { static constexpr int TW = RPGO_S3_TW, G = RPGO_S3_G, SEG = RPGO_S3_SEG, SEG_SMALL = 64, MINB = RPGO_S3_MINB; };
+template <> struct TileShape<2, MODE_SIMPLE> { static constexpr int TW = 8, G = 2, SEG = 512, SEG_SMALL = 64, MINB = RPGO_S2_MINB; };
+
+template <int D, int MODE>
+static void launch_mode(GroupView g, const double* aos, const double* soa, int j_begin, Shard sh, Thresholds th, Flagged fl,
+                        cudaStream_t st) {
+  typedef TileShape<D, MODE> S;
+  const int cb_begin = j_begin / 32;
+  const int cb_end = (g.n + 31) / 32;
+  /* online case: a handful of new closures against a large group -> lanes over the older closures */
+  if (g.n - j_begin <= 32 && j_begin >= 32) {
+    launch_column<D, MODE>(g, aos, soa, j_begin, sh, th, fl, st);
+    return;
+  }
+  /* few work items (small groups, or a handful of new columns in the online case): short row segments, so that the
+   * launch fills the SMs and a block is a few iterations long (latency of a single-closure update) */
+  const long long items = (long long)((g.n + S::SEG - 1) / S::SEG) * (cb_end - cb_begin);
+  if (items < 4LL * 148 * S::MINB)
+    launch_grouped<D, MODE, S::TW, S::G, S::SEG_SMALL, S::MINB>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st);
+  else
+    launch_grouped<D, MODE, S::TW, S::G, S::SEG, S::MINB>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st);
 }
 
 void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, const double* soa, int j_begin, Shard sh,
                            Thresholds th, Flagged fl, int variant, cudaStream_t st) {
-  (void)mode; /* MODE_PCM only */
   if (g.n < 2 || j_begin >= g.n) return;
-  const int cb_begin = j_begin / 32;
-  const int cb_end = (g.n + 31) / 32;
-  dim3 grid((g.n + TILE_SEG - 1) / TILE_SEG, cb_end - cb_begin);
-  if (variant != 0) {
+  if (variant != 0 && mode == MODE_PCM) {
     /* cross-check forms for the parity tests: one warp group, straight-line (1) or plain branchy (2) pair function */
+    const int cb_begin = j_begin / 32;
+    const int cb_end = (g.n + 31) / 32;
+    dim3 grid((g.n + TILE_SEG - 1) / TILE_SEG, cb_end - cb_begin);
     if (dim == 3) {
       if (variant == 1) launch_variant<3, 12, 1, 2>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st);
       else launch_variant<3, 12, 1, 1>(g, aos, soa, j_begin, cb_begin, grid, sh, th, fl, st);
@@ -483,23 +583,13 @@ void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, co
     }
     return;
   }
-  /* online case: a handful of new closures against a large group -> lanes over the older closures */
-  if (g.n - j_begin <= 32 && j_begin >= 32) {
-    if (dim == 3) launch_column<3>(g, aos, soa, j_begin, sh, th, fl, st);
-    else launch_column<2>(g, aos, soa, j_begin, sh, th, fl, st);
-    return;
+  if (mode == MODE_PCM) {
+    if (dim == 3) launch_mode<3, MODE_PCM>(g, aos, soa, j_begin, sh, th, fl, st);
+    else launch_mode<2, MODE_PCM>(g, aos, soa, j_begin, sh, th, fl, st);
+  } else {
+    if (dim == 3) launch_mode<3, MODE_SIMPLE>(g, aos, soa, j_begin, sh, th, fl, st);
+    else launch_mode<2, MODE_SIMPLE>(g, aos, soa, j_begin, sh, th, fl, st);
   }
-  /* few work items (small groups, or a handful of new columns in the online case): short row segments, so that the
-   * launch fills the SMs and a block is 4 iterations long instead of 43 (latency of a single-closure update) */
-  const long long items512 = (long long)((g.n + TILE_SEG - 1) / TILE_SEG) * (cb_end - cb_begin);
-  const bool small = items512 < 4LL * 148;
-  if (small) {
-    if (dim == 3) launch_grouped<3, 12, 3, 48>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st);
-    else launch_grouped<2, 12, 3, 48>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st);
-    return;
-  }
-  if (dim == 3) launch_grouped<3, 12, 3, 504>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st); /* 42 x 12 rows: no ragged last iteration */
-  else launch_grouped<2, 12, 3, 512>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st);
 }
 
 }  // namespace rpgo

@@ -217,6 +217,58 @@ RPGO_FN void hsht(const Adj<D>& H, LoadS S, double* out) {
   }
 }
 
+/* M <- H M H^T in place, the same entries as hsht() (every entry keeps its own k-order chain, so the bits are
+ * identical): first T = H M column by column (a column of T depends only on the same column of M), then T H^T row by
+ * row.  Only M, H and 12 temporaries are live instead of two full matrices. */
+template <int D>
+RPGO_FN void hsht_inplace(const Adj<D>& H, double* M) {
+  if (D == 3) {
+    const double* A = H.h;
+    const double* B = H.h + 9;
+    RPGO_UNROLL
+    for (int c = 0; c < 6; ++c) {
+      const double s0 = M[c], s1 = M[6 + c], s2 = M[12 + c], s3 = M[18 + c], s4 = M[24 + c], s5 = M[30 + c];
+      RPGO_UNROLL
+      for (int r = 0; r < 3; ++r) M[r * 6 + c] = dot3(A[r * 3], A[r * 3 + 1], A[r * 3 + 2], s0, s1, s2);
+      RPGO_UNROLL
+      for (int r = 0; r < 3; ++r) {
+        double acc = dot3(B[r * 3], B[r * 3 + 1], B[r * 3 + 2], s0, s1, s2);
+        acc = fma(A[r * 3], s3, acc);
+        acc = fma(A[r * 3 + 1], s4, acc);
+        acc = fma(A[r * 3 + 2], s5, acc);
+        M[(3 + r) * 6 + c] = acc;
+      }
+    }
+    RPGO_UNROLL
+    for (int i = 0; i < 6; ++i) {
+      const double t0 = M[i * 6], t1 = M[i * 6 + 1], t2 = M[i * 6 + 2], t3 = M[i * 6 + 3], t4 = M[i * 6 + 4], t5 = M[i * 6 + 5];
+      RPGO_UNROLL
+      for (int j = 0; j < 3; ++j) M[i * 6 + j] = dot3(t0, t1, t2, A[j * 3], A[j * 3 + 1], A[j * 3 + 2]);
+      RPGO_UNROLL
+      for (int j = 0; j < 3; ++j) {
+        double acc = dot3(t0, t1, t2, B[j * 3], B[j * 3 + 1], B[j * 3 + 2]);
+        acc = fma(t3, A[j * 3], acc);
+        acc = fma(t4, A[j * 3 + 1], acc);
+        acc = fma(t5, A[j * 3 + 2], acc);
+        M[i * 6 + 3 + j] = acc;
+      }
+    }
+  } else {
+    RPGO_UNROLL
+    for (int c = 0; c < 3; ++c) {
+      const double s0 = M[c], s1 = M[3 + c], s2 = M[6 + c];
+      RPGO_UNROLL
+      for (int r = 0; r < 3; ++r) M[r * 3 + c] = dot3(H.h[r * 3], H.h[r * 3 + 1], H.h[r * 3 + 2], s0, s1, s2);
+    }
+    RPGO_UNROLL
+    for (int i = 0; i < 3; ++i) {
+      const double t0 = M[i * 3], t1 = M[i * 3 + 1], t2 = M[i * 3 + 2];
+      RPGO_UNROLL
+      for (int j = 0; j < 3; ++j) M[i * 3 + j] = dot3(t0, t1, t2, H.h[j * 3], H.h[j * 3 + 1], H.h[j * 3 + 2]);
+    }
+  }
+}
+
 /* Eigen::LLT unblocked (lower): 1 = Success, 0 = NumericalIssue (a pivot <= 0) */
 template <int N>
 RPGO_FN bool llt_ok(const double* Min) {

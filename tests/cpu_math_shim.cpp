@@ -65,6 +65,29 @@ static int pair_v2_t(const double* Ta, const double* Tb, const double* lci, cons
   return ok;
 }
 
+/* straight-line PcmSimple pair function on the tiled kernel's compact entries (pose, rotation_info, node) */
+template <int D>
+static int pair_simple_v2_t(const double* Ta, const double* Tb, const double* lci, const double* Tc, const double* Td,
+                            const double* lcj, const double* thr, double* dist, int* near, int* bad, int exact) {
+  Thresholds th;
+  th.odom = thr[0]; th.lc = thr[1]; th.odom_trans = thr[2]; th.odom_rot = thr[3]; th.dist_trans = thr[4];
+  th.dist_rot = thr[5]; th.band = 1e-9;
+  const double* in[6] = {Ta, Tb, lci, Tc, Td, lcj};
+  double c[6][SimpleEntry<D>::E];
+  for (int k = 0; k < 6; ++k) {
+    for (int i = 0; i < Dim<D>::PS; ++i) c[k][i] = in[k][i];
+    c[k][SimpleEntry<D>::OFF_ROT] = in[k][Dim<D>::OFF_ROT];
+    c[k][SimpleEntry<D>::OFF_NODE] = in[k][Dim<D>::OFF_NODE];
+  }
+  bool nr, bd = false;
+  bool ok;
+  if (exact) ok = pair_check_simple_exact<D>(c[0], 1, c[1], 1, c[2], 1, c[3], 1, c[4], 1, c[5], 1, th, dist, &nr);
+  else ok = pair_check_simple_v2<D>(c[0], 1, c[1], 1, c[2], 1, c[3], 1, c[4], 1, c[5], 1, th, dist, &nr, &bd);
+  *near = nr;
+  *bad = bd;
+  return ok;
+}
+
 #define DISPATCH(d, m, F, ...)                                   \
   ((d) == 3 ? ((m) == 0 ? F<3, 0>(__VA_ARGS__) : F<3, 1>(__VA_ARGS__)) \
             : ((m) == 0 ? F<2, 0>(__VA_ARGS__) : F<2, 1>(__VA_ARGS__)))
@@ -93,6 +116,11 @@ int shim_pair_check_v1(int d, const double* Ta, const double* Tb, const double* 
 int shim_pair_check_v2(int d, const double* Ta, const double* Tb, const double* lci, const double* Tc,
                        const double* Td, const double* lcj, const double* thr, double* dist, int* bad) {
   return d == 3 ? pair_v2_t<3>(Ta, Tb, lci, Tc, Td, lcj, thr, dist, bad) : pair_v2_t<2>(Ta, Tb, lci, Tc, Td, lcj, thr, dist, bad);
+}
+int shim_pair_check_simple_v2(int d, const double* Ta, const double* Tb, const double* lci, const double* Tc, const double* Td,
+                              const double* lcj, const double* thr, double* dist, int* near, int* bad, int exact) {
+  return d == 3 ? pair_simple_v2_t<3>(Ta, Tb, lci, Tc, Td, lcj, thr, dist, near, bad, exact)
+                : pair_simple_v2_t<2>(Ta, Tb, lci, Tc, Td, lcj, thr, dist, near, bad, exact);
 }
 void shim_compose(int d, int mode, const double* a, const double* b, double* o) { DISPATCH(d, mode, compose_t, a, b, o); }
 void shim_between(int d, int mode, const double* a, const double* b, double* o) { DISPATCH(d, mode, between_t, a, b, o); }

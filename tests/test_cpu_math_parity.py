@@ -18,7 +18,8 @@ SO = os.path.join(ROOT, "tests", "_cpu_math_shim.so")
 def shim():
     src = os.path.join(ROOT, "tests", "cpu_math_shim.cpp")
     hdr = os.path.join(ROOT, "kimera-rpgo_b200", "csrc", "rpgo_math.cuh")
-    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdr2 = os.path.join(ROOT, "kimera-rpgo_b200", "csrc", "rpgo_pair_v2.cuh")
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(hdr2)):
         fma = ["-mfma"] if "fma" in open("/proc/cpuinfo").read() else []
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++"] + fma +
                               ["-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "kimera-rpgo_b200", "csrc"),
@@ -28,6 +29,7 @@ def shim():
     L.shim_pair_check.restype = C.c_int
     L.shim_pair_check_v1.restype = C.c_int
     L.shim_pair_check_v2.restype = C.c_int
+    L.shim_pair_check_simple_v2.restype = C.c_int
     return L
 
 
@@ -126,6 +128,7 @@ def test_pair_check_simple_bitwise(shim, d):
     n = orc.ndim(d)
     L = orc.lib()
     thr = np.array([1.0, 3.0, 1, 1, 0.05, 0.01])
+    n_flag = [0]
     for t in range(300):
         P = [rand_pose(rng, d, 1.0) for _ in range(6)]
         nodes = rng.integers(0, 50, size=4)
@@ -145,6 +148,16 @@ def test_pair_check_simple_bitwise(shim, d):
         ok = shim.shim_pair_check(d, 1, *[dp(e) for e in E], dp(thr), C.byref(dist), C.byref(near))
         assert dist.value == wt, (t, dist.value, wt)
         assert bool(ok) == bool(wt < thr[4] and wr < thr[5])
+        # the tiled kernel's forms on compact entries: exact fallback == general code; straight-line form either flags
+        # the lane or agrees bit for bit (distance, decision, near flag)
+        for exact in (1, 0):
+            d2 = C.c_double(); near2 = C.c_int(); bad = C.c_int()
+            ok2 = shim.shim_pair_check_simple_v2(d, *[dp(e) for e in E], dp(thr), C.byref(d2), C.byref(near2), C.byref(bad), exact)
+            if exact or not bad.value:
+                assert (d2.value == wt) or (np.isnan(d2.value) and np.isnan(wt)), (t, exact, d2.value, wt)
+                assert bool(ok2) == bool(ok) and near2.value == near.value
+            n_flag[0] += bad.value
+    assert n_flag[0] < 60, n_flag   # zero hop counts (nodes drawn equal) and the like: flagged, never wrong
 
 
 def test_div_by_equals_ieee_division(shim):

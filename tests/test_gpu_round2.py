@@ -260,3 +260,66 @@ def test_config4_stated_size_groups_and_fmc():
         assert res[gi][0] == kr and res[gi][1].tolist() == ir.tolist(), gi
     assert total >= 33 * 11000
     g.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tiled kernels of the other pair functions (PcmSimple3D / PcmSimple2D / Pcm2D)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d", [3, 2])
+def test_simple_tiled_kernel_equals_direct_kernel(d):
+    """PcmSimple through the TMA-tiled kernel (compact records, straight-line pair function + exact fallback) and through the
+    plain direct kernel: same bitset, flagged pairs and inliers, incl. incremental growth and the online column kernel."""
+    if d == 3:
+        gph = synth.config4(seed=19, robots=2, P=700, n=1500, outlier_frac=0.4)
+        params = dict(odom_trans=2.0, odom_rot=1.0, dist_trans=0.4, dist_rot=0.08)
+    else:
+        gph = synth.config3(seed=16, P=2000, n=1200)
+        params = dict(odom_trans=-1, odom_rot=-1, dist_trans=0.3, dist_rot=0.05)
+    res = []
+    for kern in (pkg.KERNEL_DIRECT, pkg.KERNEL_TILED):
+        g = PcmGpu(d, pkg.MODE_SIMPLE, kernel=kern, **params)
+        g.update(gph["odom"], gph["values"])
+        half = len(gph["lcs"]) // 2
+        g.update(gph["lcs"][:half], [])
+        g.update(gph["lcs"][half:half + 7], [])          # column-mode kernel on the larger groups
+        g.update(gph["lcs"][half + 7:], [])
+        res.append(g)
+    a, b = res
+    assert a.groups() == b.groups() and sum(x[2] for x in a.groups()) > 500
+    dens = []
+    for gi in range(len(a.groups())):
+        ba, bb = a.group_bits(gi), b.group_bits(gi)
+        assert np.array_equal(ba, bb), gi
+        na, pa = a.flagged(gi)
+        nb, pb = b.flagged(gi)
+        assert na == nb and sorted(map(tuple, pa.tolist())) == sorted(map(tuple, pb.tolist()))
+        assert a.group_inlier_ids(gi).tolist() == b.group_inlier_ids(gi).tolist()
+        n_ = a.groups()[gi][2]
+        dens.append(a.degrees(gi).sum() / max(1, n_ * (n_ - 1)))
+    assert 0.01 < max(dens) < 0.99, dens   # the thresholds really separate consistent from inconsistent pairs
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("d,mode", [(3, 1), (2, 1), (2, 0)])
+def test_other_modes_sampled_oracle_at_10k(d, mode):
+    """PcmSimple3D / PcmSimple2D / Pcm2D at n = 10 000 closures: 3e5 sampled pairs against the CPU oracle"""
+    n = 10000
+    if d == 3:
+        arr = synth.as_arrays(synth.config2(seed=6, P=n, n=n))
+    else:
+        arr = synth.as_arrays(synth.config3(seed=7, P=n, n=n))
+    if mode == 1:
+        params = dict(odom_trans=-1, odom_rot=-1, dist_trans=0.5 if d == 3 else 0.3, dist_rot=0.1 if d == 3 else 0.05)
+    else:
+        params = dict(odom_threshold=-1.0, lc_threshold=3.0)
+    g = PcmGpu(d, mode, **params)
+    g.odom_append_arrays(arr["o_prev"], arr["o_new"], arr["o_pose"], arr["o_cov"], arr["o_init"])
+    g.lc_append_arrays(arr["l_from"], arr["l_to"], arr["l_pose"], arr["l_cov"])
+    rows = g.group_bits(0)
+    rng = np.random.default_rng(17)
+    pi, pj = pt.sample_pairs(rng, n, 300_000)
+    want, _, _ = pt.oracle_pairs(d, mode, params, arr, pi, pj)
+    got = pt.bits_at(rows, pi, pj)
+    assert int((want != got).sum()) == 0
+    assert 0.001 < got.mean() < 0.999
+    g.close()
