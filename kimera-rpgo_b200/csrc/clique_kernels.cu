@@ -464,8 +464,11 @@ __global__ void heu_prepare_kernel(const uint32_t* __restrict__ bits, int64_t st
   heu_prepare_body(bits, stride32, n, deg, M_prev, M, invalidate != 0, degmask, cset, dead_flags);
 }
 
+#ifndef RPGO_HEU_MINB /* resident blocks per SM the compiler has to leave room for (128-thread blocks) */
+#define RPGO_HEU_MINB 5
+#endif
 template <int TH>
-__global__ void __launch_bounds__(TH) heu_round_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n,
+__global__ void __launch_bounds__(TH, TH == HEU_THREADS ? RPGO_HEU_MINB : 1) heu_round_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n,
                                                                 const int32_t* __restrict__ deg,
                                                                 const uint32_t* __restrict__ degmask, int first, int vstep,
                                                                 int M, ull* ctl, int32_t* picks_block, int32_t* dead_flags) {
@@ -490,7 +493,7 @@ struct HeuResult {
 };
 
 template <int TH>
-__global__ void __launch_bounds__(TH) heu_persistent_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n,
+__global__ void __launch_bounds__(TH, TH == HEU_THREADS ? RPGO_HEU_MINB : 1) heu_persistent_kernel(const uint32_t* __restrict__ bits, int64_t stride32, int n,
                                                                      const int32_t* __restrict__ deg, uint32_t* degmask,
                                                                      int first, int maxclq0, ull* ctl,
                                                                      int32_t* picks_block, int32_t* dead_flags,

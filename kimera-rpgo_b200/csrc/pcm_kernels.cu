@@ -835,6 +835,10 @@ void launch_mirror(uint32_t* bits, int64_t stride32, int n, int j_begin, cudaStr
   const int tiles = (n + MIRROR_T - 1) / MIRROR_T;
   const int tc_begin = j_begin / MIRROR_T;
   const int patches_x = (tiles - tc_begin + MIRROR_PATCH - 1) / MIRROR_PATCH, patches_y = (tiles + MIRROR_PATCH - 1) / MIRROR_PATCH;
+#ifdef RPGO_MIRROR_CARVEOUT
+  static PerDeviceOnce once;
+  if (once.first()) cudaFuncSetAttribute(mirror_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, RPGO_MIRROR_CARVEOUT);
+#endif
   mirror_tile_kernel<<<patches_x * patches_y * MIRROR_PATCH * MIRROR_PATCH, 256, 0, st>>>(bits, stride32, n, tc_begin, tiles, patches_x);
 }
 
