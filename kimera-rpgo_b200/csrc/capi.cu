@@ -208,7 +208,7 @@ struct Group {
   int64_t cap = 0;       /* capacity in closures (multiple of 128) */
   int64_t stride32 = 0;  /* adjacency row stride in 32-bit words (= cap / 32) */
   DevBuf lc, idxf, idxb, pfx, bits, deg, fl_pairs, fl_count;
-  DevBuf rec_aos, rec_soa; /* gathered per-closure records for the tiled kernel */
+  DevBuf rec_aos, rec_soa, rec_col; /* gathered per-closure records for the tiled kernel: rows, SoA slabs, per-lane columns */
   bool landmark = false;   /* N3: observations of one landmark instead of closures of one prefix pair */
   uint64_t lkey = 0;
   DevBuf idxa0;
@@ -218,7 +218,7 @@ struct Group {
   std::vector<int32_t> h_idxf, h_idxb;
   std::vector<uint8_t> h_pfx;
   explicit Group(Arena* a) {
-    for (DevBuf* b : {&lc, &idxf, &idxb, &pfx, &bits, &deg, &fl_pairs, &fl_count, &rec_aos, &rec_soa, &idxa0}) b->arena = a;
+    for (DevBuf* b : {&lc, &idxf, &idxb, &pfx, &bits, &deg, &fl_pairs, &fl_count, &rec_aos, &rec_soa, &rec_col, &idxa0}) b->arena = a;
   }
 };
 
@@ -362,6 +362,8 @@ static int ensure_group(rpgo_handle* h, Group* g, int64_t need) {
     const size_t rn = (size_t)tiled_record_doubles(h->dim, h->mode) * 8;
     H_CHECK_CUDA(h, g->rec_aos.ensure((size_t)ncap * rn + 256, (size_t)g->n * rn, st));
     H_CHECK_CUDA(h, g->rec_soa.ensure((size_t)ncap * rn + 256, (size_t)((g->n + 31) / 32) * 32 * rn, st));
+    const size_t cn = (size_t)tiled_column_pitch(h->dim, h->mode) * 8;
+    H_CHECK_CUDA(h, g->rec_col.ensure((size_t)ncap * cn + 256, (size_t)g->n * cn, st));
   }
   if (h->loop_check || g->landmark) {
     /* adjacency: ncap rows x ncap/32 words; the row pitch changes, so copy row by row (2D copy) */
@@ -415,12 +417,12 @@ static int run_pairwise(rpgo_handle* h, Group* g, int64_t j_begin, double* dist_
   if (kernel == RPGO_KERNEL_TILED) {
     if (g->gathered < g->n) {
       launch_gather_records(h->dim, h->mode, v, h->traj.as<double>(), (int)g->gathered, g->rec_aos.as<double>(),
-                            g->rec_soa.as<double>(), h->stream);
+                            g->rec_soa.as<double>(), g->rec_col.as<double>(), h->stream);
       g->gathered = g->n;
       h->launches += 1;
     }
-    launch_pairwise_tiled(h->dim, h->mode, v, g->rec_aos.as<double>(), g->rec_soa.as<double>(), (int)j_begin, sh, h->th,
-                          group_flagged(g), variant, h->stream);
+    launch_pairwise_tiled(h->dim, h->mode, v, g->rec_aos.as<double>(), g->rec_soa.as<double>(), g->rec_col.as<double>(), (int)j_begin,
+                          sh, h->th, group_flagged(g), variant, h->stream);
   } else
     launch_pairwise_direct(h->dim, h->mode, v, h->traj.as<double>(), (int)j_begin, sh, h->th, group_flagged(g), dist_dev,
                            h->stream);

@@ -75,11 +75,13 @@ void launch_scatter_entries(int dim, int n, const double* entries, const uint64_
 void launch_pairwise_direct(int dim, int mode, GroupView g, const double* traj, int j_begin, Shard sh, Thresholds th,
                             Flagged fl, double* dist_out, cudaStream_t st);
 int tiled_record_doubles(int dim, int mode);
-void launch_gather_records(int dim, int mode, GroupView g, const double* traj, int k0, double* aos, double* soa, cudaStream_t st);
+int tiled_column_pitch(int dim, int mode); /* doubles per record of the per-lane column array */
+void launch_gather_records(int dim, int mode, GroupView g, const double* traj, int k0, double* aos, double* soa, double* col,
+                           cudaStream_t st);
 /* variant: 0 = default (phase-shifted warp groups, straight-line pair function); the two cross-check forms
  * RPGO_KERNEL_TILED_ONE_GROUP / RPGO_KERNEL_TILED_V1 select 1 / 2 */
-void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, const double* soa, int j_begin, Shard sh,
-                           Thresholds th, Flagged fl, int variant, cudaStream_t st);
+void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, const double* soa, const double* col, int j_begin,
+                           Shard sh, Thresholds th, Flagged fl, int variant, cudaStream_t st);
 /* N3: landmark re-observation matrix (one thread per pair of observations of the same landmark) */
 void launch_landmark_direct(int dim, int mode, GroupView g, const double* traj, int j_begin, Thresholds th, Flagged fl,
                             double* dist_out, cudaStream_t st);

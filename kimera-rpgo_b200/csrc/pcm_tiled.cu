@@ -37,6 +37,11 @@ struct Rec {
   static constexpr int N = 3 * E + 2; /* doubles per record (16-byte multiple) */
   static constexpr int OFF_TF = 0, OFF_TB = E, OFF_LC = 2 * E, OFF_PFX = 3 * E;
   static constexpr int SCR = MODE == MODE_PCM ? Dim<D>::ENTRY : 0; /* per-thread scratch doubles (b_odom_d of the PCM chain) */
+  /* Column records: one record per LANE, array-of-structs with an ODD pitch in doubles.  Every field then sits at a
+   * compile-time offset from the lane's base (no per-load address arithmetic: 550 of 6020 instructions per pair in the
+   * strided layout), and 16 lanes x 8 bytes at a pitch of CP doubles hit 16 different bank pairs (CP mod 16 is odd). */
+  static constexpr int CP = (N % 2 == 0) ? N + 1 : N;
+  static constexpr int SP = (SCR % 2 == 0) ? SCR + 1 : SCR; /* per-thread scratch pitch, odd for the same reason */
 };
 static_assert(Rec<3, MODE_SIMPLE>::N % 2 == 0 && Rec<2, MODE_SIMPLE>::N % 2 == 0 && Rec<3>::N % 2 == 0 && Rec<2>::N % 2 == 0,
               "bulk copies move 16-byte units");
@@ -48,8 +53,8 @@ int tiled_record_doubles(int dim, int mode) {
 
 /* ---- gather -------------------------------------------------------------------------------------- */
 template <int D, int MODE>
-__global__ void gather_records_kernel(GroupView g, const double* __restrict__ traj, int k0, double* aos, double* soa) {
-  constexpr int E = Rec<D, MODE>::E, RN = Rec<D, MODE>::N, TE = Dim<D>::ENTRY;
+__global__ void gather_records_kernel(GroupView g, const double* __restrict__ traj, int k0, double* aos, double* soa, double* col) {
+  constexpr int E = Rec<D, MODE>::E, RN = Rec<D, MODE>::N, TE = Dim<D>::ENTRY, CP = Rec<D, MODE>::CP;
   const int k = k0 + blockIdx.x;
   if (k >= g.n) return;
   for (int f = threadIdx.x; f < RN; f += blockDim.x) {
@@ -66,6 +71,7 @@ __global__ void gather_records_kernel(GroupView g, const double* __restrict__ tr
     }
     aos[(size_t)k * RN + f] = v;
     soa[((size_t)(k >> 5) * RN + f) * 32 + (k & 31)] = v;
+    col[(size_t)k * CP + f] = v;
   }
 }
 
@@ -101,6 +107,18 @@ __device__ __forceinline__ bool row_owned_t(const Shard& sh, int i) {
   const int64_t c = i / sh.chunk_rows;
   return c == sh.rank || c == 2 * (int64_t)sh.world - 1 - sh.rank;
 }
+
+/* shared memory of the grouped kernel: column slab as 32 per-lane records (pitch CP), row stages (pitch N), per-thread
+ * scratch records (pitch SP) */
+template <int D, int TILE_WARPS, int MODE>
+struct GroupedSmem {
+  typedef Rec<D, MODE> R;
+  static constexpr size_t JT = (size_t)R::CP * 32 * 8;
+  static constexpr size_t IT = (size_t)2 * TILE_WARPS * R::N * 8;
+  static constexpr size_t SCR = (size_t)R::SP * (R::SCR ? 1 : 0) * TILE_WARPS * 32 * 8;
+  static constexpr size_t BYTES = JT + IT + SCR + 256;
+  static_assert(JT % 16 == 0 && IT % 16 == 0 && SCR % 8 == 0, "bulk-copy destinations are 16-byte aligned");
+};
 
 /* exact general paths for the rare lanes the straight-line code flags (kept out of line: cold code) */
 template <int D>
@@ -261,11 +279,11 @@ __device__ __forceinline__ void group_of(int w, int& grp, int& wi) {
 #endif
 template <int D, int MODE, int TILE_WARPS, int G, int SEG, int MINB>
 __global__ void __launch_bounds__(RPGO_K3_LB_THREADS(TILE_WARPS), MINB)
-    pairwise_grouped_kernel(GroupView g, const double* __restrict__ aos, const double* __restrict__ soa, int j_begin,
+    pairwise_grouped_kernel(GroupView g, const double* __restrict__ aos, const double* __restrict__ col, int j_begin,
                             int cb_begin, Shard sh, Thresholds th, Flagged fl) {
   typedef Rec<D, MODE> R;
-  typedef TiledSmem<D, TILE_WARPS, MODE> SM;
-  constexpr int RN = R::N;
+  typedef GroupedSmem<D, TILE_WARPS, MODE> SM;
+  constexpr int RN = R::N, CP = R::CP, SP = R::SP;
   constexpr int WG = TILE_WARPS / G;
   static_assert(WG * G == TILE_WARPS, "groups must divide the block");
   static_assert(1 + 2 * G <= 32, "mbarrier slots");
@@ -295,7 +313,7 @@ __global__ void __launch_bounds__(RPGO_K3_LB_THREADS(TILE_WARPS), MINB)
   __syncthreads();
   if (tid == 0) {
     mbar_expect_tx(&bars[0], (uint32_t)SM::JT);
-    tma_load_1d(Jt, soa + (size_t)cb * RN * 32, (uint32_t)SM::JT, &bars[0]);
+    tma_load_1d(Jt, col + (size_t)cb * CP * 32, (uint32_t)SM::JT, &bars[0]); /* the slab's 32 records are contiguous */
   }
   const bool leader = (wi == 0 && lane == 0);
   double* Ig = It + (size_t)grp * 2 * WG * RN;       /* this group's two stages */
@@ -309,9 +327,9 @@ __global__ void __launch_bounds__(RPGO_K3_LB_THREADS(TILE_WARPS), MINB)
   mbar_wait(&bars[0], 0);
 
   const int j = cb * 32 + lane;
-  const double* Jl = Jt + lane;
-  const uint8_t pc = (uint8_t)Jl[R::OFF_PFX * 32];
-  double* scr = Scr + tid;
+  const double* Jl = Jt + (size_t)lane * CP;  /* this lane's column record: field f at Jl[f] */
+  const uint8_t pc = (uint8_t)Jl[R::OFF_PFX];
+  double* scr = Scr + (size_t)tid * SP;       /* this thread's scratch record */
 
   int it = 0;
   for (int base = first; base < r_end; base += TILE_WARPS, ++it) {
@@ -330,22 +348,22 @@ __global__ void __launch_bounds__(RPGO_K3_LB_THREADS(TILE_WARPS), MINB)
       if (j < g.n && j > i && j >= j_begin) {
         const uint8_t pa = (uint8_t)Ir[R::OFF_PFX];
         /* Pcm.h:691-698: if the prefixes of a and c differ, c and d swap (measurement not inverted) */
-        const double* Tc = (pa != pc) ? Jl + R::OFF_TB * 32 : Jl + R::OFF_TF * 32;
-        const double* Td = (pa != pc) ? Jl + R::OFF_TF * 32 : Jl + R::OFF_TB * 32;
+        const double* Tc = (pa != pc) ? Jl + R::OFF_TB : Jl + R::OFF_TF;
+        const double* Td = (pa != pc) ? Jl + R::OFF_TF : Jl + R::OFF_TB;
         bool near;
         /* the 6x6 chain is called directly: through the tile_pair wrapper ptxas spills 8 more bytes per thread and the 3D
          * kernel loses 2 % (measured, profiles/r2_k3_variants.md) */
         if constexpr (MODE == MODE_PCM) {
           double dist;
           bool bad;
-          ok = pair_check_v2<D>(Ir + R::OFF_TF, 1, Ir + R::OFF_TB, 1, Ir + R::OFF_LC, 1, Tc, 32, Td, 32,
-                                Jl + R::OFF_LC * 32, 32, scr, TILE_WARPS * 32, th, &dist, &near, &bad);
+          ok = pair_check_v2<D>(Ir + R::OFF_TF, 1, Ir + R::OFF_TB, 1, Ir + R::OFF_LC, 1, Tc, 1, Td, 1, Jl + R::OFF_LC, 1, scr, 1, th,
+                                &dist, &near, &bad);
           if (bad)
-            ok = pair_check_exact<D>(Ir + R::OFF_TF, 1, Ir + R::OFF_TB, 1, Ir + R::OFF_LC, 1, Tc, 32, Td, 32,
-                                     Jl + R::OFF_LC * 32, 32, scr, TILE_WARPS * 32, &th, &dist, &near);
+            ok = pair_check_exact<D>(Ir + R::OFF_TF, 1, Ir + R::OFF_TB, 1, Ir + R::OFF_LC, 1, Tc, 1, Td, 1, Jl + R::OFF_LC, 1, scr, 1,
+                                     &th, &dist, &near);
         } else
-          ok = tile_pair<D, MODE>(Ir + R::OFF_TF, 1, Ir + R::OFF_TB, 1, Ir + R::OFF_LC, 1, Tc, 32, Td, 32, Jl + R::OFF_LC * 32, 32, scr,
-                                TILE_WARPS * 32, th, &near);
+          ok = tile_pair<D, MODE>(Ir + R::OFF_TF, 1, Ir + R::OFF_TB, 1, Ir + R::OFF_LC, 1, Tc, 1, Td, 1, Jl + R::OFF_LC, 1, scr, 1, th,
+                                  &near);
         if (near) {
           const unsigned long long slot = atomicAdd(fl.count, 1ULL);
           if ((int64_t)slot < fl.cap) {
@@ -428,14 +446,20 @@ static void launch_column(GroupView g, const double* aos, const double* soa, int
   pairwise_column_kernel<D, MODE, TW><<<grid, TW * 32, smem, st>>>(g, aos, soa, j_begin, sh, th, fl);
 }
 
-void launch_gather_records(int dim, int mode, GroupView g, const double* traj, int k0, double* aos, double* soa, cudaStream_t st) {
+int tiled_column_pitch(int dim, int mode) {
+  if (mode == MODE_PCM) return dim == 3 ? Rec<3>::CP : Rec<2>::CP;
+  return dim == 3 ? Rec<3, MODE_SIMPLE>::CP : Rec<2, MODE_SIMPLE>::CP;
+}
+
+void launch_gather_records(int dim, int mode, GroupView g, const double* traj, int k0, double* aos, double* soa, double* col,
+                           cudaStream_t st) {
   if (k0 >= g.n) return;
   if (mode == MODE_PCM) {
-    if (dim == 3) gather_records_kernel<3, MODE_PCM><<<g.n - k0, 160, 0, st>>>(g, traj, k0, aos, soa);
-    else gather_records_kernel<2, MODE_PCM><<<g.n - k0, 64, 0, st>>>(g, traj, k0, aos, soa);
+    if (dim == 3) gather_records_kernel<3, MODE_PCM><<<g.n - k0, 160, 0, st>>>(g, traj, k0, aos, soa, col);
+    else gather_records_kernel<2, MODE_PCM><<<g.n - k0, 64, 0, st>>>(g, traj, k0, aos, soa, col);
   } else {
-    if (dim == 3) gather_records_kernel<3, MODE_SIMPLE><<<g.n - k0, 64, 0, st>>>(g, traj, k0, aos, soa);
-    else gather_records_kernel<2, MODE_SIMPLE><<<g.n - k0, 32, 0, st>>>(g, traj, k0, aos, soa);
+    if (dim == 3) gather_records_kernel<3, MODE_SIMPLE><<<g.n - k0, 64, 0, st>>>(g, traj, k0, aos, soa, col);
+    else gather_records_kernel<2, MODE_SIMPLE><<<g.n - k0, 32, 0, st>>>(g, traj, k0, aos, soa, col);
   }
 }
 
@@ -502,19 +526,19 @@ static void launch_variant(GroupView g, const double* aos, const double* soa, in
 }
 
 template <int D, int MODE, int TW, int G, int SEG, int MINB>
-static void launch_grouped(GroupView g, const double* aos, const double* soa, int j_begin, int cb_begin, int cb_end, Shard sh,
+static void launch_grouped(GroupView g, const double* aos, const double* col, int j_begin, int cb_begin, int cb_end, Shard sh,
                            Thresholds th, Flagged fl, cudaStream_t st) {
   static PerDeviceOnce once;
   if (once.first()) {
     cudaFuncSetAttribute(pairwise_grouped_kernel<D, MODE, TW, G, SEG, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)TiledSmem<D, TW, MODE>::BYTES);
+                         (int)GroupedSmem<D, TW, MODE>::BYTES);
     /* MINB blocks per SM only materialise if the shared-memory carve-out is large enough for all of them */
     cudaFuncSetAttribute(pairwise_grouped_kernel<D, MODE, TW, G, SEG, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
   }
   dim3 grid((g.n + SEG - 1) / SEG, cb_end - cb_begin);
-  pairwise_grouped_kernel<D, MODE, TW, G, SEG, MINB><<<grid, TW * 32, TiledSmem<D, TW, MODE>::BYTES, st>>>(g, aos, soa, j_begin, cb_begin,
-                                                                                                       sh, th, fl);
+  pairwise_grouped_kernel<D, MODE, TW, G, SEG, MINB><<<grid, TW * 32, GroupedSmem<D, TW, MODE>::BYTES, st>>>(g, aos, col, j_begin,
+                                                                                                         cb_begin, sh, th, fl);
 }
 
 /* Block shapes per pair function (measured, profiles/r2_*): the 6x6 chain needs 168 registers and 50 doubles of scratch per
@@ -547,8 +571,8 @@ template <> struct TileShape<3, MODE_SIMPLE> { static constexpr int TW = RPGO_S3
 template <> struct TileShape<2, MODE_SIMPLE> { static constexpr int TW = 8, G = 2, SEG = 512, SEG_SMALL = 64, MINB = RPGO_S2_MINB; };
 
 template <int D, int MODE>
-static void launch_mode(GroupView g, const double* aos, const double* soa, int j_begin, Shard sh, Thresholds th, Flagged fl,
-                        cudaStream_t st) {
+static void launch_mode(GroupView g, const double* aos, const double* soa, const double* col, int j_begin, Shard sh, Thresholds th,
+                        Flagged fl, cudaStream_t st) {
   typedef TileShape<D, MODE> S;
   const int cb_begin = j_begin / 32;
   const int cb_end = (g.n + 31) / 32;
@@ -561,13 +585,13 @@ static void launch_mode(GroupView g, const double* aos, const double* soa, int j
    * launch fills the SMs and a block is a few iterations long (latency of a single-closure update) */
   const long long items = (long long)((g.n + S::SEG - 1) / S::SEG) * (cb_end - cb_begin);
   if (items < 4LL * 148 * S::MINB)
-    launch_grouped<D, MODE, S::TW, S::G, S::SEG_SMALL, S::MINB>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st);
+    launch_grouped<D, MODE, S::TW, S::G, S::SEG_SMALL, S::MINB>(g, aos, col, j_begin, cb_begin, cb_end, sh, th, fl, st);
   else
-    launch_grouped<D, MODE, S::TW, S::G, S::SEG, S::MINB>(g, aos, soa, j_begin, cb_begin, cb_end, sh, th, fl, st);
+    launch_grouped<D, MODE, S::TW, S::G, S::SEG, S::MINB>(g, aos, col, j_begin, cb_begin, cb_end, sh, th, fl, st);
 }
 
-void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, const double* soa, int j_begin, Shard sh,
-                           Thresholds th, Flagged fl, int variant, cudaStream_t st) {
+void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, const double* soa, const double* col, int j_begin,
+                           Shard sh, Thresholds th, Flagged fl, int variant, cudaStream_t st) {
   if (g.n < 2 || j_begin >= g.n) return;
   if (variant != 0 && mode == MODE_PCM) {
     /* cross-check forms for the parity tests: one warp group, straight-line (1) or plain branchy (2) pair function */
@@ -584,11 +608,11 @@ void launch_pairwise_tiled(int dim, int mode, GroupView g, const double* aos, co
     return;
   }
   if (mode == MODE_PCM) {
-    if (dim == 3) launch_mode<3, MODE_PCM>(g, aos, soa, j_begin, sh, th, fl, st);
-    else launch_mode<2, MODE_PCM>(g, aos, soa, j_begin, sh, th, fl, st);
+    if (dim == 3) launch_mode<3, MODE_PCM>(g, aos, soa, col, j_begin, sh, th, fl, st);
+    else launch_mode<2, MODE_PCM>(g, aos, soa, col, j_begin, sh, th, fl, st);
   } else {
-    if (dim == 3) launch_mode<3, MODE_SIMPLE>(g, aos, soa, j_begin, sh, th, fl, st);
-    else launch_mode<2, MODE_SIMPLE>(g, aos, soa, j_begin, sh, th, fl, st);
+    if (dim == 3) launch_mode<3, MODE_SIMPLE>(g, aos, soa, col, j_begin, sh, th, fl, st);
+    else launch_mode<2, MODE_SIMPLE>(g, aos, soa, col, j_begin, sh, th, fl, st);
   }
 }
 

@@ -1,9 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
+: > gpurun_out/variants.jsonl
+run() { RPGO_LIB_PATH=$1 timeout 300 python tools/k3_probe.py $2 $3 $4 >> gpurun_out/variants.jsonl 2>> gpurun_out/variants.err; }
 P=kimera-rpgo_b200/librpgo_b200.so
-V=kimera-rpgo_b200/variants
-for L in $P $V/librpgo_b200_heu5.so $V/librpgo_b200_heu6.so $V/librpgo_b200_heu8.so $V/librpgo_b200_mir100.so $V/librpgo_b200_mir75.so; do
-  echo "== $L"; RPGO_LIB_PATH=$L timeout 300 python tools/clique_probe.py 50000
-done
-for L in $P $V/librpgo_b200_heu6.so $V/librpgo_b200_heu8.so; do echo "== $L 200k"; RPGO_LIB_PATH=$L timeout 300 python tools/clique_probe.py 200000; done
-timeout 600 ncu --set full --clock-control none -f -k regex:"mirror_tile|heu_persistent" -c 4 -o gpurun_out/r2_mirror_heu_v2 python tools/clique_probe.py 50000 > gpurun_out/ncu_clique2.log 2>&1; tail -2 gpurun_out/ncu_clique2.log
+B=kimera-rpgo_b200/variants/librpgo_b200_base.so
+for L in $B $P; do run $L 3 0 20000; run $L 3 0 50000; run $L 2 0 20000; run $L 3 1 20000; run $L 2 1 20000; done
+cat gpurun_out/variants.jsonl; tail -3 gpurun_out/variants.err
+timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -m gpu -q -x -k "not stated and not config5 and not config4 and not clique" > gpurun_out/n1e_pytest.log 2>&1
+echo "pytest rc=$?"; tail -4 gpurun_out/n1e_pytest.log
