@@ -545,7 +545,7 @@ static void launch_grouped(GroupView g, const double* aos, const double* col, in
  * thread, so one 12-warp block fills an SM; the 3x3 chain and the pose-only PcmSimple chains are small enough for 2-3
  * blocks of 8 warps per SM, which is what hides their dependency latency. */
 #ifndef RPGO_2D_MINB
-#define RPGO_2D_MINB 3
+#define RPGO_2D_MINB 4
 #endif
 #ifndef RPGO_S3_MINB
 #define RPGO_S3_MINB 3
