@@ -319,7 +319,7 @@ def main():
     g.lib.rpgo_fp64_peak(local, C.byref(tf))
     k3_ms = k3 / a.steps
     achieved = FLOP_PER_PAIR["pcm3d"] * (pairs / world) / (k3_ms * 1e-3) / 1e12
-    kname = {0: "pairwise_grouped_kernel<3,12,3,504>", 1: "pairwise_direct_kernel<3,0,2>", 2: "pairwise_grouped_kernel<3,12,3,504>",
+    kname = {0: "pairwise_grouped_kernel<3,PCM,12,3,504,1>", 1: "pairwise_direct_kernel<3,PCM,2>", 2: "pairwise_grouped_kernel<3,PCM,12,3,504,1>",
              24: "pairwise_tiled_kernel<3,12,1,2>", 22: "pairwise_tiled_kernel<3,12,1,1>"}.get(a.kernel, "?")
     roofline = {"bound": "fp64", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s", "frac": achieved / tf.value,
                 "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_nominal": achieved / FP64_NOMINAL_TFLOPS,

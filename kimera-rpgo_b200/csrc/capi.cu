@@ -907,6 +907,7 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
 
   /* host pass 2: grouping in arrival order (Pcm.h:466-486) */
   std::map<int32_t, int64_t> old_n; /* groups touched -> size before this call */
+  const size_t groups_at_entry = h->groups.size();
   std::vector<int64_t> need(h->groups.size(), 0);
   for (int64_t k = 0; k < n; ++k) {
     if (odom_dist) odom_dist[k] = dist_host[k];
@@ -951,6 +952,30 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
     need.resize(h->groups.size(), 0);
   }
   mark("grouping (host)");
+  /* From here on the host bookkeeping (group sizes, key vectors, possibly new groups) is ahead of the device state.  If
+   * an allocation, copy or launch fails the bookkeeping is rolled back, so the handle stays usable and consistent with the
+   * caller's own lists (the reference has no failure mode here). */
+  auto rollback = [&](size_t first_new_group) {
+    for (auto& kv : old_n) {
+      if ((size_t)kv.first >= first_new_group) continue;
+      Group* g = h->groups[kv.first];
+      g->n = kv.second;
+      g->kfrom.resize((size_t)kv.second);
+      g->kto.resize((size_t)kv.second);
+      g->h_idxf.resize((size_t)kv.second);
+      g->h_idxb.resize((size_t)kv.second);
+      g->h_pfx.resize((size_t)kv.second);
+      if (g->gathered > g->n) g->gathered = g->n;
+    }
+    while (h->groups.size() > first_new_group) {
+      Group* g = h->groups.back();
+      h->gindex.erase({g->id1, g->id2});
+      delete g;
+      h->groups.pop_back();
+    }
+  };
+  const size_t first_new_group = groups_at_entry;
+  auto device_part = [&]() -> int {
   /* capacities (n was advanced above; ensure_group must see the old n for its copies) */
   for (auto& kv : old_n) {
     Group* g = h->groups[kv.first];
@@ -1003,6 +1028,14 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
   H_CHECK_CUDA(h, cudaStreamSynchronize(st)); /* host vectors / pinned staging are reused */
   mark("final sync");
   return RPGO_OK;
+  };
+  const int rc_dev = device_part();
+  if (rc_dev != RPGO_OK) {
+    cudaStreamSynchronize(st);
+    cudaGetLastError();
+    rollback(first_new_group);
+  }
+  return rc_dev;
 }
 
 int rpgo_landmark_append(rpgo_handle* h, uint64_t landmark_key, int64_t n, const uint64_t* pose_key, const double* pose,

@@ -555,7 +555,11 @@ static void launch_grouped(GroupView g, const double* aos, const double* col, in
 #endif
 template <int D, int MODE>
 struct TileShape;
-template <> struct TileShape<3, MODE_PCM> { static constexpr int TW = 12, G = 3, SEG = 504, SEG_SMALL = 48, MINB = 1; };
+#ifndef RPGO_3D_G
+#define RPGO_3D_G 3
+#define RPGO_3D_SEG 504
+#endif
+template <> struct TileShape<3, MODE_PCM> { static constexpr int TW = 12, G = RPGO_3D_G, SEG = RPGO_3D_SEG, SEG_SMALL = 48, MINB = 1; };
 #ifndef RPGO_2D_TW
 #define RPGO_2D_TW 8
 #define RPGO_2D_G 2

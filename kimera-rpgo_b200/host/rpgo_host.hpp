@@ -448,8 +448,20 @@ class PcmGpu : public OutlierRemovalT<P> {
     for (auto& m : groups_) total_good_lc_ += m.consistent_factors.size();
   }
   void findInliersIncremental(const std::map<int, size_t>& num_new) {                // Pcm.h:906-947
-    for (auto& kv : num_new)
-      selectInliers(kv.first, RPGO_CLIQUE_HEU_INCREMENTAL, (int64_t)kv.second, (int64_t)groups_[kv.first].consistent_factors.size(), true);
+    for (auto& kv : num_new) {
+      Group& m = groups_[kv.first];
+      if (!loop_check_ && !m.is_landmark) {
+        // the reference runs findMaxCliqueHeuIncremental on the 1x1 zero matrix the disabled check leaves behind
+        // (Pcm.h:484-486): vertex 0 is selected only when exactly one closure is new and nothing was selected before
+        if (kv.second == 1 && m.consistent_factors.size() == 0) {
+          m.consistent_factors = Graph();
+          m.consistent_factors.add(m.factors[0]);
+          m.inlier_idx.assign(1, 0);
+        }
+        continue;
+      }
+      selectInliers(kv.first, RPGO_CLIQUE_HEU_INCREMENTAL, (int64_t)kv.second, (int64_t)m.consistent_factors.size(), true);
+    }
     for (size_t g = 0; g < groups_.size(); ++g)
       if (groups_[g].is_landmark && groups_[g].factors.size() > 0) selectInliers((int)g, RPGO_CLIQUE_HEU, 0, 0, false);   // Pcm.h:950-966
     total_good_lc_ = 0;
@@ -461,7 +473,21 @@ class PcmGpu : public OutlierRemovalT<P> {
     check(rpgo_lc_remove_last(h_, g, &k1, &k2), "rpgo_lc_remove_last");
     m.factors.pop_back();
     if (m.factors.size() < 2) m.consistent_factors = m.factors;                      // Pcm.h:316-317
-    else selectInliers(g, RPGO_CLIQUE_HEU, 0, 0, false);
+    else if (!loop_check_ && !m.is_landmark) {
+      // no adjacency exists when the pairwise check is disabled; the reference's path (0x0 block into findMaxCliqueHeu) is
+      // undefined behaviour.  Defined as findInliers' rule for that configuration (Pcm.h:870-873): every factor an inlier;
+      // incremental mode keeps the previous selection, clipped to the remaining factors
+      if (params_.incremental) {
+        Graph kept;
+        for (size_t i = 0; i < m.inlier_idx.size(); ++i)
+          if ((size_t)m.inlier_idx[i] < m.factors.size()) kept.add(m.factors[m.inlier_idx[i]]);
+        m.consistent_factors = kept;
+        m.inlier_idx.erase(std::remove_if(m.inlier_idx.begin(), m.inlier_idx.end(), [&](int32_t i) { return (size_t)i >= m.factors.size(); }),
+                           m.inlier_idx.end());
+      } else {
+        m.consistent_factors = m.factors;
+      }
+    } else selectInliers(g, RPGO_CLIQUE_HEU, 0, 0, false);
     *updated = buildGraphToOptimize();
     return EdgePtr(new Edge(k1, k2));
   }

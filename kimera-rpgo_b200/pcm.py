@@ -409,6 +409,16 @@ class PcmGpu:
         self._landmark_inliers()
 
     def _find_inliers_incremental(self, num_new):  # Pcm.h:906-970
+        if not self.loop_check:
+            # the reference still calls findMaxCliqueHeuIncremental, on the 1x1 zero matrix the disabled check leaves behind
+            # (Pcm.h:484-486): the only candidate is vertex 0, and only when exactly one closure is new and nothing was
+            # selected before (findCliqueHeu.cpp:141-145).  Nothing to compute on the GPU.
+            for g, nn in num_new.items():
+                if nn == 1 and len(self.group_consistent[g]) == 0:
+                    self.group_consistent[g] = [self.group_factors[g][0]]
+            self.total_good_lc = sum(len(self.group_consistent[g]) for g in self.group_order)
+            self._landmark_inliers()
+            return
         gs = list(num_new.keys())
         prevs = [len(self.group_consistent[g]) for g in gs]
         res = self.find_inliers_batch(gs, CLIQUE_HEU_INCREMENTAL, [num_new[g] for g in gs], prevs)
@@ -449,9 +459,17 @@ class PcmGpu:
             return None
         k1, k2 = C.c_uint64(), C.c_uint64()
         self._check(self.lib.rpgo_lc_remove_last(self.h, g, C.byref(k1), C.byref(k2)), "rpgo_lc_remove_last")
-        fs.pop()
+        removed = fs.pop()
         if len(fs) < 2:
             self.group_consistent[g] = list(fs)
+        elif not self.loop_check:
+            # no adjacency is kept when the pairwise check is disabled; the reference's own path is undefined behaviour
+            # there (0x0 block into findMaxCliqueHeu).  Defined as findInliers' rule for that configuration
+            # (Pcm.h:870-873: all factors) / "previous set minus the removed factor" in incremental mode.
+            if self.incremental:
+                self.group_consistent[g] = [f for f in self.group_consistent[g] if f != removed]
+            else:
+                self.group_consistent[g] = list(fs)
         else:
             k, ids, _ = self.find_inliers_raw(g, CLIQUE_HEU)
             self.group_consistent[g] = [fs[i] for i in ids[:k]]

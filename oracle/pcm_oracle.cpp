@@ -196,6 +196,9 @@ int find_max_clique_heu(int n, const double* adj, std::vector<int>* out) {
 /* src/utils/GraphUtils.cpp:30-44 */
 int find_max_clique_heu_incremental(int n, const double* adj, size_t num_new, size_t prev, std::vector<int>* out) {
   Csr g = csr_from_dense(n, adj);
+  /* findCliqueHeu.cpp:141: the first candidate index is computed in size_t; with more new closures than vertices (only
+   * possible when the pairwise check is disabled and the matrix stays 1x1) it wraps and the loop never runs */
+  if (num_new > (size_t)n) return 0;
   const int r = heu_restated(g, n - (int)num_new, (int)prev, out);
   if ((size_t)r > prev) return r;
   return 0;
@@ -589,10 +592,22 @@ struct Oracle {
     if (num_lc == 0) return 0; /* reference would index factors[-1]; guarded */
     *k1 = m.factors[num_lc - 1].k1;
     *k2 = m.factors[num_lc - 1].k2;
+    const int64_t removed_id = m.factors[num_lc - 1].id;
     m.factors.pop_back();
     if (m.factors.size() < 2) {
       m.consistent.clear();
       for (auto& f : m.factors) m.consistent.push_back(f.id);
+    } else if (!loop_check) {
+      /* With the pairwise check disabled the reference's matrices stay 1x1 (Pcm.h:484-486), so Pcm.h:320-323 takes a
+       * 0x0 block and findMaxCliqueHeu returns -1 as a size_t: undefined behaviour.  Defined here (and in the product's
+       * host mirrors) as what findInliers does in that configuration (Pcm.h:870-873: every factor is an inlier); in
+       * incremental mode the previous inlier set is kept, minus the removed factor. */
+      if (incremental) {
+        m.consistent.erase(std::remove(m.consistent.begin(), m.consistent.end(), removed_id), m.consistent.end());
+      } else {
+        m.consistent.clear();
+        for (auto& f : m.factors) m.consistent.push_back(f.id);
+      }
     } else {
       std::vector<double> adj, dist;
       dense(m, &adj, &dist);

@@ -69,3 +69,19 @@ def test_exact_matches_reference_fmc():
         # the exact finder returns a true clique
         s = ir.tolist()
         assert all(a[x, y] for x in s for y in s if x != y)
+
+
+def test_incremental_on_the_1x1_matrix_of_a_disabled_loop_check():
+    """With the pairwise check disabled the reference never grows its matrices (Pcm.h:484-486), so findInliersIncremental
+    runs FMC on a 1x1 zero matrix with num_new >= 1: vertex 0 is selected only for num_new == 1 and prev == 0; for
+    num_new > n the size_t candidate index wraps and nothing is selected (findCliqueHeu.cpp:141).  Pinned on the
+    reference's own code when it is built, and on the restatement."""
+    z = np.zeros((1, 1), dtype=np.uint8)
+    impls = [orc.clique_heu_incremental]
+    if orc.ref_fmc() is not None:
+        impls.append(orc.ref_clique_heu_incremental)
+    for f in impls:
+        k, ids = f(z, 1, 0)
+        assert k == 1 and ids.tolist() == [0]
+        assert f(z, 1, 1)[0] == 0
+        assert f(z, 3, 0)[0] == 0

@@ -323,3 +323,24 @@ def test_other_modes_sampled_oracle_at_10k(d, mode):
     assert int((want != got).sum()) == 0
     assert 0.001 < got.mean() < 0.999
     g.close()
+
+
+@pytest.mark.parametrize("first", [1, 3])
+def test_disabled_loop_check_incremental_and_remove_last(first):
+    """lc_threshold < 0 with incremental mode / removeLastLoopClosure must not raise; behaviour = the reference's
+    (FMC on the never-grown 1x1 matrix) where it is defined, findInliers' all-inliers rule where the reference is UB."""
+    gph = synth.config2(seed=3, P=300, n=12)
+    for inc in (True, False):
+        params = dict(odom_threshold=-1, lc_threshold=-1, incremental=inc)
+        g, o = PcmGpu(3, 0, **params), orc.OraclePcm(3, 0, **params)
+        for x in (g, o):
+            x.update(gph["odom"], gph["values"])
+            x.update(gph["lcs"][:first], [])
+            x.update(gph["lcs"][first:first + 1], [])
+            x.update(gph["lcs"][first + 1:first + 4], [])
+        assert g.num_inliers() == o.num_inliers() and g.group_inlier_ids(0).tolist() == o.group_inlier_ids(0).tolist()
+        assert g.output_ids().tolist() == o.output_ids().tolist()
+        assert g.remove_last() == o.remove_last()
+        assert g.group_inlier_ids(0).tolist() == o.group_inlier_ids(0).tolist()
+        assert g.output_ids().tolist() == o.output_ids().tolist()
+        g.close()
