@@ -361,6 +361,313 @@ __global__ void __launch_bounds__(64) traj_fold_batched_kernel(int n_chains, con
   }
 }
 
+
+/* K1, pipelined exact fold (MODE_PCM).  Same arithmetic, same order as traj_fold_batched_kernel (bit-identical); the
+ * sequential path of a step is reduced to the dependent FP64 chain plus the exchange of the running covariance:
+ *   - three warps: warp 0 folds the covariance, warp 1 the pose, warp 2 is the producer: it copies the factors of block
+ *     b+2 global -> shared (cp.async, three raw slots) and builds Ad(delta^-1) + the rotation_info flag of block b+1 while
+ *     the chain warps fold block b (the batched kernel prepared a block between two chain phases);
+ *   - the chain warps read the delta covariance / pose / output slot straight from the raw slot (the NaN mask of
+ *     from_factor is one select per element) and fetch the operands of step i+1 before the dependent part of step i;
+ *   - RPGO_FOLD_XCHG selects how the covariance is exchanged between the two products of H S H^T:
+ *       0  shuffles (18 + 18 SHFL per step, as in the batched kernel)
+ *       1  two shared-memory hops: S column-major (a lane reads its two columns with 6 LDS.128), H S row-major
+ *       2  one hop: every lane reads the whole S and recomputes the row of H S it needs. */
+#ifndef RPGO_FOLD_XCHG
+#define RPGO_FOLD_XCHG 1
+#endif
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int K>
+__device__ __forceinline__ void cp_async_wait_le() { asm volatile("cp.async.wait_group %0;" ::"n"(K) : "memory"); }
+
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) { /* a value the compiler may not re-derive inside a loop */
+  uint32_t o;
+  asm volatile("mov.u32 %0, %1;" : "=r"(o) : "r"(v));
+  return o;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void lds_f64x2(uint32_t a, double& x, double& y) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a) : "memory");
+}
+__device__ __forceinline__ int lds_s32(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void stg_f64x2(double* p, double x, double y) {
+  asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ double sel_f64(bool c, double x, double y) {
+  double o;
+  asm("{ .reg .pred p; setp.ne.s32 p, %3, 0; selp.f64 %0, %1, %2, p; }" : "=d"(o) : "d"(x), "d"(y), "r"((int)c));
+  return o;
+}
+
+template <int D>
+__global__ void __launch_bounds__(96) traj_fold_pipelined_kernel(int n_chains, const FoldChain* __restrict__ chains,
+                                                                 const int32_t* __restrict__ out_idx,
+                                                                 const double* __restrict__ dpose,
+                                                                 const double* __restrict__ dcov, double* entries) {
+  constexpr int E = Dim<D>::ENTRY, PS = Dim<D>::PS, N = Dim<D>::N, NN = N * N, OC = Dim<D>::OFF_COV, RD = Dim<D>::RD,
+                TD = Dim<D>::TD, HS = (D == 3 ? 18 : 9), B = 32, CPL = (D == 3 ? 2 : 1);
+  __shared__ __align__(16) double raw_pose[3][B * PS];
+  __shared__ __align__(16) double raw_cov[3][B * NN];
+  __shared__ __align__(16) double cH[2][B * HS];
+  __shared__ __align__(16) double xs[NN];
+  __shared__ __align__(16) double xt[NN];
+  __shared__ int raw_out[3][B];
+  __shared__ int cRot[2][B];
+  const int c = blockIdx.x;
+  if (c >= n_chains) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const FoldChain ch = chains[c];
+  if (ch.n_steps <= 0) return;
+  const int nb = (ch.n_steps + B - 1) / B;
+
+  auto issue_raw = [&](int b) { /* producer warp */
+    if (b < nb) {
+      const int slot = b % 3;
+      const size_t k0 = (size_t)ch.first_step + (size_t)b * B;
+      const int cnt = min(B, ch.n_steps - b * B);
+      for (int i = lane; i < cnt * PS; i += 32) cp_async8(&raw_pose[slot][i], dpose + k0 * PS + i);
+      for (int i = lane; i < cnt * NN; i += 32) cp_async8(&raw_cov[slot][i], dcov + k0 * NN + i);
+      if (lane < cnt) cp_async4(&raw_out[slot][lane], out_idx + k0 + lane);
+    }
+    cp_async_commit(); /* one group per block index, empty past the end: keeps the wait counts uniform */
+  };
+  auto prep = [&](int b) { /* producer warp: everything of block b that does not depend on the running value */
+    if (b >= nb) return;
+    const int slot = b % 3, st = b & 1;
+    const int cnt = min(B, ch.n_steps - b * B);
+    if (lane < cnt) {
+      Pose<D> Dl;
+#pragma unroll
+      for (int i = 0; i < PS; ++i) Dl.m[i] = raw_pose[slot][lane * PS + i];
+      double tr = raw_cov[slot][lane * NN];
+#pragma unroll
+      for (int i = 1; i < RD; ++i) tr = tr + raw_cov[slot][lane * NN + i * N + i];
+      cRot[st][lane] = (tr != tr) ? 0 : 1;
+      const Adj<D> H = adjoint<D>(inverse<D>(Dl));
+#pragma unroll
+      for (int i = 0; i < HS; ++i) cH[st][lane * HS + i] = H.h[i];
+    }
+  };
+
+  if (warp == 2) {
+    issue_raw(0);
+    issue_raw(1);
+    cp_async_wait_le<1>();
+    __syncwarp();
+    prep(0);
+  }
+  __syncthreads();
+
+  if (warp == 2) {
+    for (int b = 0; b < nb; ++b) {
+      issue_raw(b + 2);      /* slot (b+2)%3 was read by the chain warps in iteration b-1 */
+      cp_async_wait_le<1>(); /* block b+1 has landed */
+      __syncwarp();
+      prep(b + 1);
+      __syncthreads();
+    }
+    return;
+  }
+  /* The chain warps address shared memory through explicit 32-bit window addresses held in registers (the compiler
+   * otherwise re-derives them from SR_CgaCtaId inside the loop, a 25-cycle S2UR on the sequential path), keep their loop
+   * bodies free of branches (operand fetches are clamped instead of guarded; lanes without an element of their own shadow
+   * lane 0 and store the same values to the same addresses), and the loops are unrolled by two so that the operands
+   * fetched for step i+1 need no register moves. */
+  const uint32_t a_pose = opaque_u32((uint32_t)__cvta_generic_to_shared(&raw_pose[0][0]));
+  const uint32_t a_cov = opaque_u32((uint32_t)__cvta_generic_to_shared(&raw_cov[0][0]));
+  const uint32_t a_H = opaque_u32((uint32_t)__cvta_generic_to_shared(&cH[0][0]));
+  const uint32_t a_out = opaque_u32((uint32_t)__cvta_generic_to_shared(&raw_out[0][0]));
+  const uint32_t a_rot = opaque_u32((uint32_t)__cvta_generic_to_shared(&cRot[0][0]));
+  if (warp == 1) {
+    /* pose chain: every lane composes the same pose and stores it (identical values to identical addresses) */
+    Pose<D> P;
+    load_pose<D>(entries + (size_t)ch.start_idx * E, 1, P);
+    int rot = entries[(size_t)ch.start_idx * E + Dim<D>::OFF_ROT] != 0.0 ? 1 : 0;
+    for (int b = 0; b < nb; ++b) {
+      const int slot = b % 3, st = b & 1;
+      const int cnt = min(B, ch.n_steps - b * B);
+      const uint32_t bp = a_pose + slot * (B * PS * 8), bo = a_out + slot * (B * 4), br = a_rot + st * (B * 4);
+      Pose<D> Dn;
+      int rn, on;
+      auto fetch = [&](int i) {
+#pragma unroll
+        for (int q = 0; q < PS; q += 2) lds_f64x2(bp + (i * PS + q) * 8, Dn.m[q], Dn.m[q + 1]);
+        rn = lds_s32(br + i * 4);
+        on = lds_s32(bo + i * 4);
+      };
+      fetch(0);
+#pragma unroll 2
+      for (int i = 0; i < cnt; ++i) {
+        const Pose<D> Dl = Dn;
+        const int rc = rn;
+        double* o = entries + (size_t)on * E;
+        fetch(min(i + 1, cnt - 1));
+        P = compose<D>(P, Dl);
+        rot &= rc;
+#pragma unroll
+        for (int q = 0; q < PS; q += 2) stg_f64x2(o + q, P.m[q], P.m[q + 1]);
+        if ((Dim<D>::OFF_ROT & 1) == 0 && Dim<D>::OFF_NODE == Dim<D>::OFF_ROT + 1) {
+          stg_f64x2(o + Dim<D>::OFF_ROT, rot ? 1.0 : 0.0, 0.0);
+        } else {
+          o[Dim<D>::OFF_ROT] = rot ? 1.0 : 0.0;
+          o[Dim<D>::OFF_NODE] = 0.0;
+        }
+      }
+      __syncthreads();
+    }
+    return;
+  }
+  {
+    /* covariance chain: lane (r, cg) owns the elements (r, cg) and, in 3D, (r, cg + 3) */
+    const int ll = opaque_u32(lane < 3 * N ? lane : 0);
+    const int r = ll / 3, cg = ll % 3;
+    double S[CPL];
+    int keep[CPL]; /* element survives a NaN rotation covariance (translation block only) */
+#pragma unroll
+    for (int cc = 0; cc < CPL; ++cc) {
+      const int j = cg + 3 * cc;
+      S[cc] = entries[(size_t)ch.start_idx * E + OC + r * N + j];
+      keep[cc] = (r >= RD && j >= RD && r < RD + TD && j < RD + TD) ? 1 : 0;
+    }
+    const int hro = (D == 3) ? (r < 3 ? r * 3 : 9 + (r - 3) * 3) : r * 3; /* row r of H, columns 0..2 */
+    const int aro = (r < 3 ? r : r - 3) * 3;                              /* 3D rows >= 3: columns 3..5 */
+    const bool lower = (D == 3) && r >= 3;
+    const uint32_t a_xs = opaque_u32((uint32_t)__cvta_generic_to_shared(&xs[0]));
+    const uint32_t a_xt = opaque_u32((uint32_t)__cvta_generic_to_shared(&xt[0]));
+#if RPGO_FOLD_XCHG == 2
+    const uint32_t w_xs = a_xs + (r * N + cg) * 8; /* row-major S */
+#else
+    const uint32_t w_xs = a_xs + (cg * N + r) * 8; /* column-major S: element (r, cg); (r, cg + 3) is 3 N doubles further */
+    const uint32_t r_xs = a_xs + cg * N * 8;
+    const uint32_t w_xt = a_xt + (r * N + cg) * 8; /* row-major H S */
+    const uint32_t r_xt = a_xt + r * N * 8;
+#endif
+    double* const obase = entries + OC + r * N + cg;
+    for (int b = 0; b < nb; ++b) {
+      const int slot = b % 3, st = b & 1;
+      const int cnt = min(B, ch.n_steps - b * B);
+      const uint32_t bH = a_H + st * (B * HS * 8), bc = a_cov + slot * (B * NN * 8) + (r * N + cg) * 8, bo = a_out + slot * (B * 4),
+                     br = a_rot + st * (B * 4);
+      double nh[3], na[3], nA[3], nB[3], ndc[CPL];
+      double* no;
+      auto fetch = [&](int i) {
+        const uint32_t Hh = bH + i * (HS * 8);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          nh[q] = lds_f64(Hh + (hro + q) * 8);
+          nA[q] = lds_f64(Hh + (cg * 3 + q) * 8);
+          if (D == 3) { na[q] = lds_f64(Hh + (aro + q) * 8); nB[q] = lds_f64(Hh + (9 + cg * 3 + q) * 8); }
+        }
+        const int drot = lds_s32(br + i * 4);
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) {
+          const double v = lds_f64(bc + (i * NN + 3 * cc) * 8);
+          ndc[cc] = sel_f64((drot | keep[cc]) != 0, v, 0.0);
+        }
+        no = obase + (size_t)lds_s32(bo + i * 4) * E;
+      };
+      fetch(0);
+#pragma unroll 2
+      for (int i = 0; i < cnt; ++i) {
+        double h[3], a[3], A[3], Bq[3], dc[CPL];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { h[q] = nh[q]; A[q] = nA[q]; if (D == 3) { a[q] = na[q]; Bq[q] = nB[q]; } }
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) dc[cc] = ndc[cc];
+        double* o = no;
+        double tf[N];
+#if RPGO_FOLD_XCHG == 2
+        /* one hop: S row-major in shared memory, every lane recomputes row r of H S */
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) sts_f64(w_xs + 3 * cc * 8, S[cc]);
+        __syncwarp();
+        double sa[NN + 1];
+#pragma unroll
+        for (int q = 0; q < NN - 1; q += 2) lds_f64x2(a_xs + q * 8, sa[q], sa[q + 1]);
+        if (NN & 1) sa[NN - 1] = lds_f64(a_xs + (NN - 1) * 8);
+        fetch(min(i + 1, cnt - 1));
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          double t = dot3(h[0], h[1], h[2], sa[k], sa[N + k], sa[2 * N + k]);
+          if (D == 3) {
+            double t6 = fma(a[0], sa[(3 * N + k) % NN], t);
+            t6 = fma(a[1], sa[(4 * N + k) % NN], t6);
+            t6 = fma(a[2], sa[(5 * N + k) % NN], t6);
+            t = sel_f64(lower, t6, t);
+          }
+          tf[k] = t;
+        }
+        __syncwarp(); /* all reads of xs done before the next step overwrites it */
+#else
+        double t[CPL];
+        /* hop 1: S column-major; a lane reads its own columns */
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) sts_f64(w_xs + 3 * cc * N * 8, S[cc]);
+        __syncwarp();
+        double col[CPL][N + 1];
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) {
+          if (D == 3) {
+#pragma unroll
+            for (int q = 0; q < N; q += 2) lds_f64x2(r_xs + (3 * cc * N + q) * 8, col[cc][q], col[cc][q + 1]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < N; ++q) col[cc][q] = lds_f64(r_xs + q * 8);
+          }
+        }
+        fetch(min(i + 1, cnt - 1));
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) {
+          double tt = dot3(h[0], h[1], h[2], col[cc][0], col[cc][1], col[cc][2]);
+          if (D == 3) {
+            double t6 = fma(a[0], col[cc][3 % N], tt);
+            t6 = fma(a[1], col[cc][4 % N], t6);
+            t6 = fma(a[2], col[cc][5 % N], t6);
+            tt = sel_f64(lower, t6, tt);
+          }
+          t[cc] = tt;
+        }
+        /* hop 2: H S row-major; a lane reads its own row */
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) sts_f64(w_xt + 3 * cc * 8, t[cc]);
+        __syncwarp();
+        if (D == 3) {
+#pragma unroll
+          for (int j = 0; j < N; j += 2) lds_f64x2(r_xt + j * 8, tf[j], tf[(j + 1) % N]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < N; ++j) tf[j] = lds_f64(r_xt + j * 8);
+        }
+#endif
+        /* out(r, j) = (H S)(r, :) . H(j, :) + Dc(r, j) */
+        S[0] = dot3(tf[0], tf[1], tf[2], A[0], A[1], A[2]) + dc[0];
+        if (D == 3) {
+          double acc = dot3(tf[0], tf[1], tf[2], Bq[0], Bq[1], Bq[2]);
+          acc = fma(tf[3 % N], A[0], acc);
+          acc = fma(tf[4 % N], A[1], acc);
+          acc = fma(tf[5 % N], A[2], acc);
+          S[CPL - 1] = acc + dc[CPL - 1];
+        }
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) o[3 * cc] = S[cc];
+      }
+      __syncthreads();
+    }
+  }
+}
+
 void launch_traj_fold(int dim, int mode, int n_chains, const FoldChain* chains, const int32_t* out_idx,
                       const double* delta_pose, const double* delta_cov, double* entries, cudaStream_t st) {
   if (n_chains <= 0) return;
@@ -372,8 +679,14 @@ void launch_traj_fold(int dim, int mode, int n_chains, const FoldChain* chains, 
       if (dim == 3) traj_fold_warp_kernel<3><<<blocks, 32, 0, st>>>(n_chains, chains, out_idx, delta_pose, delta_cov, entries);
       else traj_fold_warp_kernel<2><<<blocks, 32, 0, st>>>(n_chains, chains, out_idx, delta_pose, delta_cov, entries);
     } else {
-      if (dim == 3) traj_fold_batched_kernel<3><<<blocks, 64, 0, st>>>(n_chains, chains, out_idx, delta_pose, delta_cov, entries);
-      else traj_fold_batched_kernel<2><<<blocks, 64, 0, st>>>(n_chains, chains, out_idx, delta_pose, delta_cov, entries);
+      static const bool v2 = getenv("RPGO_FOLD_V2") != nullptr; /* A/B knob: the two-warp batched kernel */
+      if (v2) {
+        if (dim == 3) traj_fold_batched_kernel<3><<<blocks, 64, 0, st>>>(n_chains, chains, out_idx, delta_pose, delta_cov, entries);
+        else traj_fold_batched_kernel<2><<<blocks, 64, 0, st>>>(n_chains, chains, out_idx, delta_pose, delta_cov, entries);
+      } else {
+        if (dim == 3) traj_fold_pipelined_kernel<3><<<blocks, 96, 0, st>>>(n_chains, chains, out_idx, delta_pose, delta_cov, entries);
+        else traj_fold_pipelined_kernel<2><<<blocks, 96, 0, st>>>(n_chains, chains, out_idx, delta_pose, delta_cov, entries);
+      }
     }
     return;
   }
