@@ -72,13 +72,19 @@ struct Arena {
   static constexpr size_t CHUNK = (size_t)64 << 20;
   void* alloc(size_t bytes) {
     bytes = (bytes + 255) & ~size_t(255);
-    for (size_t i = chunks.size(); i-- > 0;) { /* newest first; older chunks have room again after rewind() */
-      Chunk& c = chunks[i];
-      if (c.used + bytes <= c.cap) {
-        void* r = c.p + c.used;
-        c.used += bytes;
-        return r;
-      }
+    /* best fit over the chunks: after rewind() the same request sequence then lands in the same chunks, and a small
+     * request never takes the room a dedicated large chunk was made for (first fit did, and the large request that
+     * followed had to grow the pool: 100-300 ms outliers in repeated reset -> append -> select cycles) */
+    int best = -1;
+    for (size_t i = 0; i < chunks.size(); ++i) {
+      const Chunk& c = chunks[i];
+      if (c.used + bytes <= c.cap && (best < 0 || c.cap - c.used < chunks[best].cap - chunks[best].used)) best = (int)i;
+    }
+    if (best >= 0) {
+      Chunk& c = chunks[best];
+      void* r = c.p + c.used;
+      c.used += bytes;
+      return r;
     }
     const size_t cap = bytes > CHUNK ? bytes : CHUNK;
     void* p = nullptr;
@@ -87,9 +93,7 @@ struct Arena {
       return nullptr;
     }
     /* keep the partially used previous chunk reachable for small requests: put the big one first */
-    Chunk c{(char*)p, cap, bytes};
-    if (bytes > CHUNK / 2 && !chunks.empty()) chunks.insert(chunks.end() - 1, c);
-    else chunks.push_back(c);
+    chunks.push_back(Chunk{(char*)p, cap, bytes});
     return p;
   }
   void release() {
@@ -186,6 +190,26 @@ struct PinBuf {
   }
 };
 
+/* host -> pinned staging copies of tens of MB: one core moves ~10 GB/s, four move the 19 MB of a 50k batch in ~0.5 ms */
+static void staged_copy(void* dst, const void* src, size_t bytes) {
+  constexpr size_t MIN_PER_THREAD = (size_t)2 << 20;
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const size_t T = std::min<size_t>({(size_t)4, (size_t)hw, bytes / MIN_PER_THREAD});
+  if (T <= 1) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  const size_t per = ((bytes + T - 1) / T + 63) & ~size_t(63);
+  std::vector<std::thread> th;
+  for (size_t t = 1; t < T; ++t) {
+    const size_t off = t * per;
+    if (off >= bytes) break;
+    th.emplace_back([=]() { memcpy((char*)dst + off, (const char*)src + off, std::min(per, bytes - off)); });
+  }
+  memcpy(dst, src, std::min(per, bytes));
+  for (auto& x : th) x.join();
+}
+
 /* every entry point runs on the handle's device and leaves the caller's current device as it found it */
 struct DeviceGuard {
   int prev = -1;
@@ -226,6 +250,75 @@ constexpr int64_t FLAG_CAP = 1 << 20;
 
 }  // namespace
 
+/* key -> trajectory entry.  GTSAM keys are (chr << 56 | index): a flat open-addressing table (Fibonacci hashing, linear
+ * probing) resolves the 150 k lookups of a 50 k-closure batch in well under a millisecond; std::unordered_map needed 4-5 ms
+ * (a node allocation per insert, a pointer chase per find).  Interface: the subset of std::unordered_map the library uses. */
+class KeyMap {
+ public:
+  struct Slot { uint64_t first; int32_t second; };
+  class iterator {
+   public:
+    iterator(const Slot* p, const Slot* e) : p_(p), e_(e) { skip(); }
+    const Slot& operator*() const { return *p_; }
+    const Slot* operator->() const { return p_; }
+    iterator& operator++() { ++p_; skip(); return *this; }
+    bool operator==(const iterator& o) const { return p_ == o.p_; }
+    bool operator!=(const iterator& o) const { return p_ != o.p_; }
+   private:
+    void skip() { while (p_ != e_ && p_->first == EMPTY) ++p_; }
+    const Slot* p_;
+    const Slot* e_;
+  };
+  iterator begin() const { return iterator(slots_.data(), slots_.data() + slots_.size()); }
+  iterator end() const { return iterator(slots_.data() + slots_.size(), slots_.data() + slots_.size()); }
+  size_t size() const { return n_; }
+  void clear() { slots_.clear(); n_ = 0; shift_ = 64; }
+  void reserve(size_t n) { if (n * 2 > slots_.size()) rehash(n * 2); }
+  iterator find(uint64_t k) const {
+    const Slot* s = lookup(k);
+    return s ? iterator(s, slots_.data() + slots_.size()) : end();
+  }
+  size_t count(uint64_t k) const { return lookup(k) ? 1 : 0; }
+  int32_t& operator[](uint64_t k) {
+    if ((n_ + 1) * 2 > slots_.size()) rehash(std::max<size_t>(64, slots_.size() * 2));
+    const size_t mask = slots_.size() - 1;
+    size_t i = hash(k);
+    /* the all-ones key doubles as the empty marker; it is not a valid gtsam::Symbol (chr 0xff, index 2^56-1) */
+    while (slots_[i].first != EMPTY && slots_[i].first != k) i = (i + 1) & mask;
+    if (slots_[i].first == EMPTY) { slots_[i].first = k; slots_[i].second = 0; ++n_; }
+    return slots_[i].second;
+  }
+
+ private:
+  static constexpr uint64_t EMPTY = ~0ull;
+  size_t hash(uint64_t k) const { return (size_t)((k * 0x9E3779B97F4A7C15ull) >> shift_); }
+  const Slot* lookup(uint64_t k) const {
+    if (slots_.empty()) return nullptr;
+    const size_t mask = slots_.size() - 1;
+    size_t i = hash(k);
+    while (slots_[i].first != EMPTY) {
+      if (slots_[i].first == k) return &slots_[i];
+      i = (i + 1) & mask;
+    }
+    return nullptr;
+  }
+  void rehash(size_t want) {
+    size_t cap = 64;
+    int bits = 6;
+    while (cap < want) { cap <<= 1; ++bits; }
+    std::vector<Slot> old;
+    old.swap(slots_);
+    slots_.assign(cap, Slot{EMPTY, 0});
+    shift_ = 64 - bits;
+    n_ = 0;
+    for (const Slot& s : old)
+      if (s.first != EMPTY) (*this)[s.first] = s.second;
+  }
+  std::vector<Slot> slots_;
+  size_t n_ = 0;
+  int shift_ = 64;
+};
+
 static constexpr int64_t CLIQUE_BLOCKS = 148 * 8;
 struct CliqueSet {
   DevBuf degmask, picks, elim, result, ctl, rwork;
@@ -240,16 +333,20 @@ struct CliqueWorker {
 };
 
 struct rpgo_handle {
-  Arena arena;
+  Arena arena;   /* state: trajectory table and per-group buffers; rewound by rpgo_reset */
+  Arena scratch; /* staging and clique scratch: no state between calls, so it survives rpgo_reset untouched */
   rpgo_cfg cfg;
   int device = 0;               /* CUDA ordinal this handle lives on (every entry point switches to it) */
   rpgo::Comm* comm = nullptr;   /* NCCL communicator over the world's GPUs (rpgo_comm_init), or null */
   PinBuf pin;                   /* pinned host staging, borrowed from the process-wide cache */
+  PinBuf pin_odom[2];           /* staging of rpgo_odom_append (two, used alternately): its own buffer, so the call returns while its H2D copy and the
+                                   fold are still running and the caller stages the loop closures into `pin` meanwhile */
   int dim = 3, mode = 0, E = 50, PS = 12, NN = 36;
   bool odom_check = true, loop_check = true;
   Thresholds th;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev_stage = nullptr; /* marks the end of the last H2D copy out of the pinned staging buffer */
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr}; /* end of the last H2D copy out of pin_odom[i] */
+  int odom_turn = 0;
   std::string err;
   int64_t launches = 0;
   CliqueStats last_clique;         /* statistics of the last rpgo_find_inliers heuristic search */
@@ -259,7 +356,7 @@ struct rpgo_handle {
   /* trajectory table: entry 0 is the default-constructed T (identity, zero covariance, node 0) */
   DevBuf traj;
   int64_t traj_n = 0;
-  std::unordered_map<uint64_t, int32_t> key2idx;
+  KeyMap key2idx;
   std::set<uint8_t> prefixes; /* prefixes for which odom_trajectories_ has an entry */
   std::set<uint64_t> missing_refs; /* keys looked up by a closure while absent (default entry used) */
   bool traj_dirty = false;         /* an entry a stored closure refers to has changed since it was resolved */
@@ -276,14 +373,18 @@ struct rpgo_handle {
 
   void wire() {
     arena.st = stream;
-    for (DevBuf* b : {&traj, &d_stage, &d_lcent, &d_ok, &d_dist, &d_scan, &cset.degmask, &cset.picks, &cset.elim, &cset.result, &cset.ctl, &cset.rwork})
-      b->arena = &arena;
+    scratch.st = stream;
+    traj.arena = &arena;
+    for (DevBuf* b : {&d_stage, &d_lcent, &d_ok, &d_dist, &d_scan, &cset.degmask, &cset.picks, &cset.elim, &cset.result, &cset.ctl, &cset.rwork})
+      b->arena = &scratch;
   }
   ~rpgo_handle() {
     DeviceGuard dg(device);
     if (stream) cudaStreamSynchronize(stream);
     if (comm) rpgo::comm_destroy(comm);
     pin.give_back();
+    pin_odom[0].give_back();
+    pin_odom[1].give_back();
     for (CliqueWorker* w : workers) {
       if (w->stream) {
         cudaStreamSynchronize(w->stream);
@@ -294,10 +395,12 @@ struct rpgo_handle {
     for (Group* g : groups) delete g;
     if (stream) {
       arena.release();
+      scratch.release();
       cudaStreamSynchronize(stream);
       cudaStreamDestroy(stream);
     }
-    if (ev_stage) cudaEventDestroy(ev_stage);
+    for (cudaEvent_t e : ev_stage)
+      if (e) cudaEventDestroy(e);
   }
 };
 
@@ -544,7 +647,7 @@ int rpgo_create(const rpgo_cfg* cfg, rpgo_handle** out) {
   h->th.dist_trans = cfg->dist_trans_threshold;
   h->th.dist_rot = cfg->dist_rot_threshold;
   h->th.band = h->cfg.band;
-  h->arena.pool = library_pool(dev);
+  h->arena.pool = h->scratch.pool = library_pool(dev);
   if (!h->arena.pool) {
     delete h;
     return RPGO_ERR_CUDA;
@@ -555,7 +658,8 @@ int rpgo_create(const rpgo_cfg* cfg, rpgo_handle** out) {
     return RPGO_ERR_CUDA;
   }
   h->wire();
-  if (cudaEventCreateWithFlags(&h->ev_stage, cudaEventDisableTiming) != cudaSuccess) {
+  if (cudaEventCreateWithFlags(&h->ev_stage[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_stage[1], cudaEventDisableTiming) != cudaSuccess) {
     delete h;
     return RPGO_ERR_CUDA;
   }
@@ -594,16 +698,8 @@ int rpgo_reset(rpgo_handle* h) {
   h->prefixes.clear();
   h->missing_refs.clear();
   h->traj_dirty = false;
-  for (DevBuf* b : {&h->traj, &h->d_stage, &h->d_lcent, &h->d_ok, &h->d_dist, &h->d_scan, &h->cset.degmask, &h->cset.picks,
-                    &h->cset.elim, &h->cset.result, &h->cset.ctl, &h->cset.rwork}) {
-    b->p = nullptr;
-    b->cap = 0;
-  }
-  for (CliqueWorker* w : h->workers)
-    for (DevBuf* b : {&w->set.degmask, &w->set.picks, &w->set.elim, &w->set.result, &w->set.ctl, &w->set.rwork}) {
-      b->p = nullptr;
-      b->cap = 0;
-    }
+  h->traj.p = nullptr; /* staging buffers and clique scratch sets live in h->scratch and are kept */
+  h->traj.cap = 0;
   h->arena.rewind();
   H_CHECK_CUDA(h, h->traj.ensure((size_t)1024 * h->E * sizeof(double), 0, h->stream));
   std::vector<double> e0(h->E, 0.0);
@@ -630,21 +726,58 @@ int64_t rpgo_launch_count(rpgo_handle* h) { return h ? h->launches : 0; }
 int64_t rpgo_traj_size(rpgo_handle* h) { return h ? (int64_t)h->key2idx.size() : 0; }
 
 /* ---------------------------------------------------------------------------------------------- */
+static int odom_append_batch(rpgo_handle* h, int64_t n, const uint64_t* prev_key, const uint64_t* new_key,
+                             const double* delta_pose, const double* delta_cov, const double* init_pose);
+
 int rpgo_odom_append(rpgo_handle* h, int64_t n, const uint64_t* prev_key, const uint64_t* new_key,
                      const double* delta_pose, const double* delta_cov, const double* init_pose) {
   if (!h || n < 0) return RPGO_ERR_INVALID;
   DeviceGuard dg(h->device);
   if (n == 0) return RPGO_OK;
   if (!prev_key || !new_key || !delta_pose || !delta_cov) return RPGO_ERR_INVALID;
+  /* A long batch is fed to the exact fold in slices (exactly what a caller appending odometry in several calls does):
+   * the fold of slice i runs on the GPU while the host resolves the keys of slice i+1 and stages its factors, so the
+   * wall time is the fold's own plus one slice of host work instead of the sum of both. */
+  constexpr int64_t SLICE = 8192;
+  if (h->cfg.traj_mode != RPGO_TRAJ_FOLD || n <= SLICE + SLICE / 2)
+    return odom_append_batch(h, n, prev_key, new_key, delta_pose, delta_cov, init_pose);
+  for (int64_t k0 = 0; k0 < n; k0 += SLICE) {
+    const int64_t m = std::min(SLICE, n - k0);
+    const int rc = odom_append_batch(h, m, prev_key + k0, new_key + k0, delta_pose + (size_t)k0 * h->PS,
+                                     delta_cov + (size_t)k0 * h->NN, init_pose ? init_pose + (size_t)k0 * h->PS : nullptr);
+    if (rc != RPGO_OK) return rc;
+  }
+  return RPGO_OK;
+}
+
+static int odom_append_batch(rpgo_handle* h, int64_t n, const uint64_t* prev_key, const uint64_t* new_key,
+                             const double* delta_pose, const double* delta_cov, const double* init_pose) {
   const int E = h->E, PS = h->PS, NN = h->NN;
   cudaStream_t st = h->stream;
+
+  static const bool trace = getenv("RPGO_TRACE") != nullptr;
+  auto now_ms = []() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  };
+  double t_mark = trace ? now_ms() : 0.0;
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    const double t = now_ms();
+    fprintf(stderr, "[odom_append n=%lld] %-28s %8.3f ms\n", (long long)n, what, t - t_mark);
+    t_mark = t;
+  };
 
   /* host pass: resolve indices, seed new prefixes, build chains (Pcm.h:524-556) */
   struct Step { int32_t src; int32_t out; int64_t k; };
   std::vector<std::vector<Step>> chains;       /* steps per chain */
   std::vector<int32_t> chain_start;            /* start entry per chain */
-  std::unordered_map<uint8_t, int> open_chain; /* prefix -> chain index whose tail can be extended */
-  std::unordered_map<int, uint64_t> chain_tail_key;
+  int open_chain[256];                         /* prefix -> chain index whose tail can be extended, or -1 */
+  std::fill(open_chain, open_chain + 256, -1);
+  std::vector<uint64_t> chain_tail_key;        /* per chain: the key its last step produced */
+  bool seen_prefix[256] = {false};             /* flat mirror of h->prefixes for the per-step test */
+  for (uint8_t c : h->prefixes) seen_prefix[c] = true;
   std::set<int32_t> overwritten;               /* pre-existing entries re-written by this batch (rare) */
   std::set<int32_t> seed_idx;                  /* host-written seed entries: ready before any kernel runs */
   const int64_t first_new_entry = h->traj_n;   /* entries >= this index are produced by this batch */
@@ -655,8 +788,9 @@ int rpgo_odom_append(rpgo_handle* h, int64_t n, const uint64_t* prev_key, const 
 
   for (int64_t k = 0; k < n; ++k) {
     const uint8_t prefix = key_chr(new_key[k]);
-    if (h->prefixes.find(prefix) == h->prefixes.end()) {
+    if (!seen_prefix[prefix]) {
       /* new prefix: poses[prev_key] = (values.at(prev_key), zero cov)  Pcm.h:534-542 */
+      seen_prefix[prefix] = true;
       h->prefixes.insert(prefix);
       int32_t idx;
       auto it = h->key2idx.find(prev_key[k]);
@@ -682,21 +816,23 @@ int rpgo_odom_append(rpgo_handle* h, int64_t n, const uint64_t* prev_key, const 
       out = it->second;
       h->traj_dirty = true; /* poses[new_key] overwritten (Pcm.h:556) */
     }
-    auto oc = open_chain.find(prefix);
-    if (oc != open_chain.end() && chain_tail_key[oc->second] == prev_key[k]) {
-      chains[oc->second].push_back({src, out, k});
-      chain_tail_key[oc->second] = new_key[k];
+    const int oc = open_chain[prefix];
+    if (oc >= 0 && chain_tail_key[oc] == prev_key[k]) {
+      chains[oc].push_back({src, out, k});
+      chain_tail_key[oc] = new_key[k];
     } else {
       if ((src >= first_new_entry && !seed_idx.count(src)) || overwritten.count(src)) need_flush_order = true; /* starts from an entry another chain writes */
       chains.push_back({{src, out, k}});
       chain_start.push_back(src);
       open_chain[prefix] = (int)chains.size() - 1;
-      chain_tail_key[(int)chains.size() - 1] = new_key[k];
+      chain_tail_key.push_back(new_key[k]);
     }
     if (out < first_new_entry) overwritten.insert(out);
   }
+  mark("keys + chains (host)");
   int rc = ensure_traj(h, new_entries);
   if (rc != RPGO_OK) return rc;
+  mark("ensure_traj");
 
   /* seeds: host-built entries, uploaded before any kernel */
   if (!seeds.empty()) {
@@ -719,7 +855,9 @@ int rpgo_odom_append(rpgo_handle* h, int64_t n, const uint64_t* prev_key, const 
   const size_t bytes_pose = (size_t)n * PS * 8, bytes_cov = (size_t)n * NN * 8;
   const size_t off_cov = bytes_pose, off_out = off_cov + bytes_cov, off_chain = off_out + (size_t)n * 4;
   const size_t total = off_chain + chains.size() * sizeof(FoldChain) + 64;
-  char* pin = (char*)h->pin.ensure(total);
+  const int turn = (h->odom_turn ^= 1);
+  H_CHECK_CUDA(h, cudaEventSynchronize(h->ev_stage[turn])); /* the H2D copy that last read this buffer */
+  char* pin = (char*)h->pin_odom[turn].ensure(total);
   if (!pin) { h->err = "pinned staging allocation failed"; return RPGO_ERR_NOMEM; }
   double* p_pose = (double*)pin;
   double* p_cov = (double*)(pin + off_cov);
@@ -731,16 +869,22 @@ int rpgo_odom_append(rpgo_handle* h, int64_t n, const uint64_t* prev_key, const 
     p_chain[c].n_steps = (int32_t)chains[c].size();
     p_chain[c].start_idx = chain_start[c];
     p_chain[c].pad = 0;
-    for (const Step& s : chains[c]) {
-      memcpy(p_pose + (size_t)pos * PS, delta_pose + (size_t)s.k * PS, sizeof(double) * PS);
-      memcpy(p_cov + (size_t)pos * NN, delta_cov + (size_t)s.k * NN, sizeof(double) * NN);
-      p_out[pos] = s.out;
-      ++pos;
+    const std::vector<Step>& cs = chains[c];
+    for (size_t a = 0; a < cs.size();) {
+      /* steps that are consecutive in the input (the usual case: one robot's odometry in order) move as one block */
+      size_t b = a + 1;
+      while (b < cs.size() && cs[b].k == cs[b - 1].k + 1) ++b;
+      staged_copy(p_pose + (size_t)pos * PS, delta_pose + (size_t)cs[a].k * PS, sizeof(double) * PS * (b - a));
+      staged_copy(p_cov + (size_t)pos * NN, delta_cov + (size_t)cs[a].k * NN, sizeof(double) * NN * (b - a));
+      for (size_t q = a; q < b; ++q) p_out[pos++] = cs[q].out;
+      a = b;
     }
   }
+  mark("staging copy (host)");
   H_CHECK_CUDA(h, h->d_stage.ensure(total, 0, st));
   H_CHECK_CUDA(h, cudaMemcpyAsync(h->d_stage.p, pin, total, cudaMemcpyHostToDevice, st));
-  H_CHECK_CUDA(h, cudaEventRecord(h->ev_stage, st));
+  H_CHECK_CUDA(h, cudaEventRecord(h->ev_stage[turn], st));
+  mark("H2D enqueue");
   char* d = (char*)h->d_stage.p;
   const double* d_pose = (const double*)d;
   const double* d_cov = (const double*)(d + off_cov);
@@ -792,9 +936,9 @@ int rpgo_odom_append(rpgo_handle* h, int64_t n, const uint64_t* prev_key, const 
   }
   H_CHECK_CUDA(h, cudaGetLastError());
   h->traj_n = new_entries;
-  /* the pinned staging buffer is reused by the next call: wait for the H2D copy only, the fold itself keeps running
-   * while the caller prepares the loop closures (everything downstream is ordered on the same stream) */
-  H_CHECK_CUDA(h, cudaEventSynchronize(h->ev_stage));
+  /* no wait here: the H2D copy out of pin_odom and the fold keep running while the caller prepares the loop closures
+   * (everything downstream is ordered on the same stream; the next rpgo_odom_append waits for ev_stage before it
+   * overwrites the buffer) */
   return RPGO_OK;
 }
 
@@ -867,8 +1011,8 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
                total = o_dst + (size_t)n * 8;
   char* pin = (char*)h->pin.ensure(total + (size_t)n * 9 + 64);
   if (!pin) { h->err = "pinned staging allocation failed"; return RPGO_ERR_NOMEM; }
-  memcpy(pin, pose, (size_t)n * PS * 8);
-  memcpy(pin + o_cov, cov, (size_t)n * NN * 8);
+  staged_copy(pin, pose, (size_t)n * PS * 8);
+  staged_copy(pin + o_cov, cov, (size_t)n * NN * 8);
   int32_t* p_if = (int32_t*)(pin + o_if);
   int32_t* p_ib = (int32_t*)(pin + o_ib);
   uint8_t* p_ck = (uint8_t*)(pin + o_ck);
@@ -1274,7 +1418,7 @@ int rpgo_find_inliers_batch(rpgo_handle* h, int32_t n_groups, const int32_t* gro
   int T = (int)std::min<size_t>(8, std::max<size_t>(1, ((size_t)2 << 30) / std::max<size_t>(per_set, 1)));
   T = std::min(T, (n_groups + world - 1) / world);
   while ((int)h->workers.size() < T) {
-    CliqueWorker* w = new CliqueWorker(&h->arena);
+    CliqueWorker* w = new CliqueWorker(&h->scratch);
     if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) { delete w; h->err = "stream creation failed"; return RPGO_ERR_CUDA; }
     h->workers.push_back(w);
   }

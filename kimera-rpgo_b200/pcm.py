@@ -33,6 +33,71 @@ class RpgoError(RuntimeError):
     pass
 
 
+class IdList:
+    """A list of factor ids / group ordinals whose bulk appends from the array entry points (numpy arrays, ranges) stay
+    as chunks until a list operation needs the elements: a 50 000-closure batch then costs microseconds of host
+    bookkeeping instead of building (and later freeing) 50 000 Python integers per list."""
+    __slots__ = ("_l", "_chunks", "_n")
+
+    def __init__(self, it=()):
+        self._l = list(it)
+        self._chunks = []
+        self._n = len(self._l)
+
+    def _flush(self):
+        if self._chunks:
+            for c in self._chunks:
+                self._l.extend(c.tolist() if isinstance(c, np.ndarray) else c)
+            self._chunks = []
+        return self._l
+
+    def extend(self, it):
+        if isinstance(it, (np.ndarray, range)):
+            if len(it):
+                self._chunks.append(it)
+                self._n += len(it)
+        else:
+            self._flush().extend(it)
+            self._n = len(self._l)
+
+    def append(self, x):
+        self._flush().append(x)
+        self._n += 1
+
+    def pop(self):
+        v = self._flush().pop()
+        self._n -= 1
+        return v
+
+    def index(self, x):
+        return self._flush().index(x)
+
+    def __len__(self):
+        return self._n
+
+    def __iter__(self):
+        return iter(self._flush())
+
+    def __getitem__(self, i):
+        if self._chunks and isinstance(i, (int, np.integer)):
+            j = int(i) + self._n if i < 0 else int(i)
+            if j < len(self._l):
+                return self._l[j]
+            j -= len(self._l)
+            for c in self._chunks:
+                if j < len(c):
+                    return int(c[j])
+                j -= len(c)
+            raise IndexError(i)
+        return self._flush()[i]
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+    def __repr__(self):
+        return "IdList(%r)" % (self._flush(),)
+
+
 class PcmGpu:
     """OutlierRemoval interface (OutlierRemoval.h:19-102) for Pcm2D/Pcm3D/PcmSimple2D/PcmSimple3D."""
 
@@ -75,14 +140,14 @@ class PcmGpu:
 
     def _clear_host_state(self):
         self.values = {}
-        self.nfg_odom, self.nfg_special = [], []
+        self.nfg_odom, self.nfg_special = IdList(), []
         self.special_is_prior = {}     # factor id -> prior key (for removePriorFactorsWithPrefix)
         self.group_factors = {}        # group ordinal -> [factor ids]
         self.group_consistent = {}     # group ordinal -> [factor ids]
         self.group_order = []
         self.landmark_group = {}       # landmark key -> group ordinal
         self.landmark_order = []
-        self.lc_in_order = []
+        self.lc_in_order = IdList()
         self.ignored = []
         self.total_lc = 0
         self.total_good_lc = 0
@@ -273,24 +338,37 @@ class PcmGpu:
                                             grp.ctypes.data_as(_capi.c_i32p), idx.ctypes.data_as(_capi.c_i32p), None),
                     "rpgo_lc_append")
         if ids is None:
-            ids = np.arange(self.next_id, self.next_id + n)
+            ids = range(self.next_id, self.next_id + n)
             self.next_id += n
-        ids = np.asarray(ids)
         num_new = {}
-        ok = acc.astype(bool)
-        touched = np.flatnonzero(np.bincount(grp[ok])) if ok.any() else []  # (np.unique's first call costs ~50 ms)
-        for g in touched:
-            g = int(g)
-            sel = ok & (grp == g)
+        if n > 0 and acc.all() and (grp == grp[0]).all():
+            # the common batch: everything accepted into one group -- no per-element work on the host
+            g = int(grp[0])
             if g not in self.group_factors:
-                self.group_factors[g] = []
+                self.group_factors[g] = IdList()
                 self.group_consistent[g] = []
                 self.group_order.append(g)
-            assert len(self.group_factors[g]) == int(idx[sel][0])
-            self.group_factors[g].extend(ids[sel].tolist())
-            num_new[g] = int(sel.sum())
-        self.lc_in_order.extend(grp[ok].tolist())
-        self.total_lc += int(ok.sum())
+            assert len(self.group_factors[g]) == int(idx[0])
+            self.group_factors[g].extend(ids if isinstance(ids, (range, np.ndarray)) else list(ids))
+            num_new[g] = n
+            self.lc_in_order.extend(grp)
+            self.total_lc += n
+        else:
+            ids = np.asarray(ids)
+            ok = acc.astype(bool)
+            touched = np.flatnonzero(np.bincount(grp[ok])) if ok.any() else []  # (np.unique's first call costs ~50 ms)
+            for g in touched:
+                g = int(g)
+                sel = ok & (grp == g)
+                if g not in self.group_factors:
+                    self.group_factors[g] = IdList()
+                    self.group_consistent[g] = []
+                    self.group_order.append(g)
+                assert len(self.group_factors[g]) == int(idx[sel][0])
+                self.group_factors[g].extend(ids[sel])
+                num_new[g] = int(sel.sum())
+            self.lc_in_order.extend(grp[ok])
+            self.total_lc += int(ok.sum())
         self.last_h2d_bytes = pose.nbytes + cov.nbytes + 9 * n
         self.last_d2h_bytes = n
         self.last_group, self.last_index = grp, idx   # per input closure: group ordinal / position in it (-1: rejected)
