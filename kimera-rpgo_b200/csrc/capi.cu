@@ -1017,10 +1017,12 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
   int32_t* p_ib = (int32_t*)(pin + o_ib);
   uint8_t* p_ck = (uint8_t*)(pin + o_ck);
   uint64_t* p_dst = (uint64_t*)(pin + o_dst);
+  bool any_check = false;
   for (int64_t k = 0; k < n; ++k) {
     const uint8_t cf = key_chr(key_from[k]), cb = key_chr(key_to[k]);
     const bool intra = cf == cb;
     p_ck[k] = (intra && h->odom_check) ? 1 : 0;
+    any_check = any_check || p_ck[k];
     if (p_ck[k]) h->prefixes.insert(cf); /* odom_trajectories_[chr] is created by the lookup, Pcm.h:619 */
     p_if[k] = traj_lookup(h, key_from[k]);
     p_ib[k] = traj_lookup(h, key_to[k]);
@@ -1041,12 +1043,20 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
   H_CHECK_CUDA(h, cudaGetLastError());
   uint8_t* h_ok = (uint8_t*)(pin + total);
   std::vector<double> dist_host;
-  H_CHECK_CUDA(h, cudaMemcpyAsync(h_ok, h->d_ok.p, (size_t)n, cudaMemcpyDeviceToHost, st));
-  if (odom_dist) {
-    dist_host.resize((size_t)n);
-    H_CHECK_CUDA(h, cudaMemcpyAsync(dist_host.data(), h->d_dist.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  if (any_check) {
+    H_CHECK_CUDA(h, cudaMemcpyAsync(h_ok, h->d_ok.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (odom_dist) {
+      dist_host.resize((size_t)n);
+      H_CHECK_CUDA(h, cudaMemcpyAsync(dist_host.data(), h->d_dist.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    }
+    H_CHECK_CUDA(h, cudaStreamSynchronize(st));
+  } else {
+    /* no closure of this batch is odometry-checked (check disabled, or inter-robot closures only): K2 accepts them all
+     * and reports NaN distances, so the grouping below does not wait for the trajectory fold and K2 -- it runs on the
+     * host while they are still executing, and K3 is enqueued behind them */
+    memset(h_ok, 1, (size_t)n);
+    if (odom_dist) dist_host.assign((size_t)n, std::nan(""));
   }
-  H_CHECK_CUDA(h, cudaStreamSynchronize(st));
   mark("H2D + K2 + D2H (sync)");
 
   /* host pass 2: grouping in arrival order (Pcm.h:466-486) */

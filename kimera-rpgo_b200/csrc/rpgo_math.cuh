@@ -254,17 +254,21 @@ RPGO_FN void hsht_inplace(const Adj<D>& H, double* M) {
       }
     }
   } else {
+    /* Ad(Pose2) has the last row (0, 0, 1) (adjoint<2>): row 2 of H M is row 2 of M and column 2 of (H M) H^T is column 2
+     * of H M -- the dense products 0*x + 0*y + 1*z return z exactly for finite x, y (only the sign of a zero result can
+     * differ, which no later operation observes), so 18 of the 54 operations are skipped, as the zero blocks of the
+     * Pose3 adjoint are above */
     RPGO_UNROLL
     for (int c = 0; c < 3; ++c) {
       const double s0 = M[c], s1 = M[3 + c], s2 = M[6 + c];
       RPGO_UNROLL
-      for (int r = 0; r < 3; ++r) M[r * 3 + c] = dot3(H.h[r * 3], H.h[r * 3 + 1], H.h[r * 3 + 2], s0, s1, s2);
+      for (int r = 0; r < 2; ++r) M[r * 3 + c] = dot3(H.h[r * 3], H.h[r * 3 + 1], H.h[r * 3 + 2], s0, s1, s2);
     }
     RPGO_UNROLL
     for (int i = 0; i < 3; ++i) {
       const double t0 = M[i * 3], t1 = M[i * 3 + 1], t2 = M[i * 3 + 2];
       RPGO_UNROLL
-      for (int j = 0; j < 3; ++j) M[i * 3 + j] = dot3(t0, t1, t2, H.h[j * 3], H.h[j * 3 + 1], H.h[j * 3 + 2]);
+      for (int j = 0; j < 2; ++j) M[i * 3 + j] = dot3(t0, t1, t2, H.h[j * 3], H.h[j * 3 + 1], H.h[j * 3 + 2]);
     }
   }
 }
