@@ -600,7 +600,10 @@ __global__ void heu_elim_kernel(const uint32_t* __restrict__ bits, int64_t strid
   if (lane == 0) elim[u] = e;
 }
 
-/* out[p], p = 1..K: the (p-1)-th smallest u with elim[u] > kstar[p] (see DESIGN.md "scratch-buffer replay") */
+/* out[p], p = 1..K: the (p-1)-th smallest u with elim[u] > kstar[p] (see DESIGN.md "scratch-buffer replay").
+ * One warp per p scans elim in ascending u.  A lane reads four consecutive entries (one 128-bit load) and four such
+ * loads are in flight per trip, so the n/32 dependent load -> ballot steps of the first version (0.5 ms at n = 50 000,
+ * one L2 latency each) become n/512 trips; elim is allocated with 64 bytes of slack and entries >= n are masked. */
 __global__ void heu_select_kernel(int n, int K, const int32_t* __restrict__ elim, const int32_t* __restrict__ kstar,
                                   int32_t* out) {
   const int p = 1 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -609,19 +612,45 @@ __global__ void heu_select_kernel(int n, int K, const int32_t* __restrict__ elim
   const int ks = kstar[p];
   int need = p - 1; /* rank to find */
   int found = -1;
-  for (int base = 0; base < n; base += 32) {
-    const int u = base + lane;
-    const bool in = (u < n) && (elim[u] > ks);
-    const unsigned m = __ballot_sync(0xffffffffu, in);
-    const int c = __popc(m);
-    if (need < c) {
-      /* the need-th set bit of m */
-      unsigned mm = m;
-      for (int i = 0; i < need; ++i) mm &= mm - 1;
-      found = base + (__ffs(mm) - 1);
-      break;
+  const int4* e4 = reinterpret_cast<const int4*>(elim);
+  const int n4 = (n + 3) >> 2; /* int4 words that hold entries < n (the tail word is padded by the allocation) */
+  for (int base4 = 0; base4 < n4 && found < 0; base4 += 128) {
+    int4 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int w = base4 + q * 32 + lane;
+      v[q] = w < n4 ? e4[w] : make_int4(INT_MIN, INT_MIN, INT_MIN, INT_MIN);
     }
-    need -= c;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (found >= 0) break;
+      const int u0 = (base4 + q * 32 + lane) * 4;
+      const bool b0 = u0 < n && v[q].x > ks, b1 = u0 + 1 < n && v[q].y > ks, b2 = u0 + 2 < n && v[q].z > ks,
+                 b3 = u0 + 3 < n && v[q].w > ks;
+      const int c = (int)b0 + (int)b1 + (int)b2 + (int)b3;
+      const int total = __reduce_add_sync(0xffffffffu, c);
+      if (need < total) {
+        /* inclusive prefix over the lanes, then the position inside the owning lane's four entries */
+        int incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += t;
+        }
+        const int excl = incl - c;
+        int mine = -1;
+        if (need >= excl && need < incl) {
+          int r = need - excl;
+          if (b0) { if (r == 0) mine = u0; --r; }
+          if (mine < 0 && b1) { if (r == 0) mine = u0 + 1; --r; }
+          if (mine < 0 && b2) { if (r == 0) mine = u0 + 2; --r; }
+          if (mine < 0 && b3) { if (r == 0) mine = u0 + 3; }
+        }
+        found = __reduce_max_sync(0xffffffffu, mine);
+      } else {
+        need -= total;
+      }
+    }
   }
   if (lane == 0) out[p] = found;
 }
