@@ -498,6 +498,16 @@ __global__ void fastmath_check_kernel(unsigned long long seed, long long per_thr
     if (!b1) { if (r != 1.0 / x) { ++bad_cnt; atomicAdd(mismatches + 2, 1ULL); } else ++ok_cnt; }
     if (!b2) { if (q != a / x) { ++bad_cnt; atomicAdd(mismatches + 3, 1ULL); } else ++ok_cnt; }
     if (!b3) { if (sq != sqrt(ax)) { ++bad_cnt; if (atomicAdd(mismatches + 4, 1ULL) == 0) { mismatches[5] = (unsigned long long)__double_as_longlong(ax); } } else ++ok_cnt; }
+    /* fused sqrt + reciprocal (LLT pivots, Logmap): s, 1/s and x/s through the Markstein correction */
+    bool b4 = false, b5 = false;
+    double rs;
+    const double s2 = opt_sqrt_rcp(ax, rs, b4);
+    const double q2 = opt_div_by(x, s2, rs, b5);
+    if (!b4) {
+      const double s_ref = sqrt(ax);
+      if (s2 != s_ref || rs != 1.0 / s_ref) { ++bad_cnt; atomicAdd(mismatches + 6, 1ULL); } else ++ok_cnt;
+      if (!b5) { if (q2 != x / s_ref) { ++bad_cnt; atomicAdd(mismatches + 7, 1ULL); } else ++ok_cnt; }
+    }
   }
   atomicAdd(mismatches, bad_cnt);
   atomicAdd(checked, ok_cnt + bad_cnt);
@@ -517,7 +527,7 @@ int fastmath_check(long long n, unsigned long long seed, unsigned long long* mis
   cudaFree(d);
   *mismatches = h[0];
   *checked = h[1];
-  if (h[0]) fprintf(stderr, "[fastmath] mismatches: rcp %llu div %llu sqrt %llu (first sqrt operand bits 0x%016llx)\n", h[2], h[3], h[4], h[5]);
+  if (h[0]) fprintf(stderr, "[fastmath] mismatches: rcp %llu div %llu sqrt %llu (first sqrt operand bits 0x%016llx) sqrt_rcp %llu div-by-sqrt %llu\n", h[2], h[3], h[4], h[5], h[6], h[7]);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
