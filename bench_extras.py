@@ -77,25 +77,34 @@ def config5(ctx):
     h = ctx["new_handle"](odom_threshold=-1.0, lc_threshold=5.0)
     st = torch.cuda.ExternalStream(h.stream_ptr(), device=ctx["device"])
     pairs = n * (n - 1) // 2
-    ctx["barrier"]()
-    t0 = time.perf_counter()
-    h.odom_append_arrays(arr["o_prev"], arr["o_new"], arr["o_pose"], arr["o_cov"], arr["o_init"])
-    h.sync()
-    t1 = time.perf_counter()
-    h.lc_append_arrays(arr["l_from"], arr["l_to"], arr["l_pose"], arr["l_cov"])
-    h.sync()
-    t2 = time.perf_counter()
-    size, ids, _ = h.find_inliers_raw(0, pkg.CLIQUE_HEU)
-    h.sync()
-    t3 = time.perf_counter()
+    cold = None
+    for it in range(2):
+        # pass 0 is the first use of the handle: it pays for ~9 GB of device allocations (5 GB of adjacency bitset, 1.9 GB of
+        # clique scratch, records) and is reported as cold_e2e_ms; pass 1 is the steady state of a long-lived solver
+        # (rpgo_reset keeps the arena), like the headline e2e
+        ctx["barrier"]()
+        t0 = time.perf_counter()
+        h.reset()
+        h.odom_append_arrays(arr["o_prev"], arr["o_new"], arr["o_pose"], arr["o_cov"], arr["o_init"])
+        h.sync()
+        t1 = time.perf_counter()
+        h.lc_append_arrays(arr["l_from"], arr["l_to"], arr["l_pose"], arr["l_cov"])
+        h.sync()
+        t2 = time.perf_counter()
+        size, ids, _ = h.find_inliers_raw(0, pkg.CLIQUE_HEU)
+        h.sync()
+        t3 = time.perf_counter()
+        if it == 0:
+            cold = (t3 - t0) * 1e3
     # kernel-only legs on the resident state
     k3 = ctx["event_ms"](torch, st, lambda: h.pairwise_only(0, 0), reps=1)
     xg = ctx["event_ms"](torch, st, lambda: h.allgather(0), reps=1)
     cl = ctx["event_ms"](torch, st, lambda: h.find_inliers_raw(0, pkg.CLIQUE_HEU), reps=1)
-    mx = ctx["max_over_ranks"]([(t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (t3 - t0) * 1e3, k3, xg, cl])
+    mx = ctx["max_over_ranks"]([(t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (t3 - t0) * 1e3, k3, xg, cl, cold])
     tf = ctx["flop"]["pcm3d"] * (pairs / ctx["world"]) / (mx[4] * 1e-3) / 1e12
     out = dict(what="3D single group n=%d (%.2e pairs) Pcm3D(odom=-1, lc=5)" % (n, float(pairs)), pairs=pairs, n_gpus=ctx["world"],
-               odom_ms=mx[0], lc_append_ms=mx[1], find_inliers_ms=mx[2], e2e_ms=mx[3], e2e_pair_checks_per_s=pairs / (mx[3] * 1e-3),
+               odom_ms=mx[0], lc_append_ms=mx[1], find_inliers_ms=mx[2], e2e_ms=mx[3], cold_e2e_ms=mx[7],
+               e2e_pair_checks_per_s=pairs / (mx[3] * 1e-3),
                k3_ms=mx[4], allgather_mirror_degree_ms=mx[5], max_clique_ms=mx[6], max_clique_size=int(size),
                pair_checks_per_s=pairs / ((mx[4] + mx[5] + mx[6]) * 1e-3), k3_tflops=tf, k3_frac_of_measured_peak=tf / ctx["peak_tflops"],
                k3_frac_of_nominal=tf / ctx["nominal"])
