@@ -241,17 +241,16 @@ def test_config4_stated_size_groups_and_fmc():
     rng = np.random.default_rng(9)
     ref = orc.ref_clique_heu if orc.ref_fmc() is not None else orc.clique_heu
     total = 0
+    o2 = orc.OraclePcm(3, 0, **params)  # one oracle, one fold of the 160 000 odometry steps, for all sampled groups
+    o2.update_arrays(arr["o_prev"], arr["o_new"], arr["o_pose"], arr["o_cov"], arr["v_keys"], arr["v_pose"])
     for gi in range(36):
         members = np.flatnonzero(grp == gi)
         order = members[np.argsort(idx[members])]
         n_ = len(order)
         rows = g.group_bits(gi)
         if gi not in whole:
-            sub = dict(arr)
-            for k in ("l_from", "l_to", "l_pose", "l_cov"):
-                sub[k] = arr[k][order]
             pi, pj = pt.sample_pairs(rng, n_, 12000)
-            want, _, _ = pt.oracle_pairs(3, 0, params, sub, pi, pj, procs=1)
+            want, _, _ = o2.check_pairs(arr["l_from"][order], arr["l_to"][order], arr["l_pose"][order], arr["l_cov"][order], pi, pj)
             assert np.array_equal(want, pt.bits_at(rows, pi, pj)), gi
             total += len(pi)
         # (3) inlier ids of every group == the reference's FMC on this adjacency
