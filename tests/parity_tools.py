@@ -51,3 +51,13 @@ def bits_at(rows, pi, pj):
     """bit (pi, pj) of packed little-endian uint64 adjacency rows"""
     w = rows[pi, pj >> 6]
     return ((w >> (pj & 63).astype(np.uint64)) & np.uint64(1)).astype(np.uint8)
+
+
+def ref_heu_worker(adj):
+    """(size, ids) of the reference's own FMC heuristic (oracle/_ref, else the oracle's restatement) on a dense 0/1 adjacency;
+    a module-level function of this light module so that spawned worker processes import nothing else"""
+    sys.path.insert(0, HERE)
+    import orc
+    f = orc.ref_clique_heu if orc.ref_fmc() is not None else orc.clique_heu
+    k, ids = f(adj)
+    return int(k), [int(x) for x in ids]
