@@ -16,6 +16,7 @@
 // GTSAM's LM/GN/GNC, src/RobustSolver.cpp:351).
 #pragma once
 
+#include <cstdio>
 #include <algorithm>
 #include <array>
 #include <cmath>
@@ -392,6 +393,12 @@ class PcmGpu : public OutlierRemovalT<P> {
     return g;
   }
   void landmarkFirst(const std::shared_ptr<Between>& f) {
+    if (f->k1 == landmarkKey(*f)) {
+      // stated landmark -> pose: the reference stores it and trips over it at the first re-observation (Pcm.h:803-808);
+      // here it is skipped with a warning before anything of this update has been applied
+      std::fprintf(stderr, "rpgo: landmark observation stated landmark -> pose skipped (must be pose -> landmark)\n");
+      return;
+    }
     const int g = landmarkAppend(f, true);
     groups_[g].factors = Graph();
     groups_[g].factors.add(std::static_pointer_cast<gtsam_lite::Factor>(f));

@@ -395,7 +395,11 @@ class PcmGpu:
         if k1 == lkey:
             # the reference stores it, then trips over it at the first re-observation (Pcm.h:803-808 returns
             # before saving the grown matrices; the next growth copies a wrongly sized block)
-            raise RpgoError("landmark observations must be stated pose -> landmark")
+            # Not an error of update(): skipped with a warning, as the reference only warns about observations it cannot
+            # use, and nothing of this call has been applied yet.
+            import warnings
+            warnings.warn("rpgo: landmark observation %d is stated landmark -> pose; skipped (observations must be pose -> landmark)" % fid)
+            return
         g = self._landmark_call(lkey, [(fid, k1, pose, cov)], reset=True)
         if lkey not in self.landmark_group:
             self.landmark_order.append(lkey)
