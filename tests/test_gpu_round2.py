@@ -349,3 +349,28 @@ def test_disabled_loop_check_incremental_and_remove_last(first):
         assert g.group_inlier_ids(0).tolist() == o.group_inlier_ids(0).tolist()
         assert g.output_ids().tolist() == o.output_ids().tolist()
         g.close()
+
+
+def test_long_odometry_batch_is_sliced_and_still_bit_exact():
+    """rpgo_odom_append feeds batches longer than 12 288 steps to the exact fold in slices of 8192 (the fold of one slice
+    overlaps the host staging of the next): the trajectory table must equal the oracle's strict left fold bit for bit, in
+    3D and 2D, including across the slice boundaries, and equal what many small appends produce."""
+    for d, gph in ((3, synth.config2(seed=8, P=20000, n=10)), (2, synth.config3(seed=8, P=20000, n=10))):
+        arr = synth.as_arrays(gph)
+        o = orc.OraclePcm(d, 0)
+        o.update_arrays(arr["o_prev"], arr["o_new"], arr["o_pose"], arr["o_cov"], arr["v_keys"], arr["v_pose"])
+        g = PcmGpu(d, 0)
+        g.odom_append_arrays(arr["o_prev"], arr["o_new"], arr["o_pose"], arr["o_cov"], arr["o_init"])
+        g2 = PcmGpu(d, 0)
+        for a in range(0, len(arr["o_prev"]), 3001):
+            sl = slice(a, a + 3001)
+            g2.odom_append_arrays(arr["o_prev"][sl], arr["o_new"][sl], arr["o_pose"][sl], arr["o_cov"][sl], arr["o_init"][sl])
+        keys = [int(k) for k in arr["o_new"]]
+        probe = keys[::397] + keys[8185:8200] + keys[16377:16392] + keys[-3:]
+        for key in probe:
+            po, co, no, ro = o.traj_get(key)
+            for h in (g, g2):
+                pg, cg, ng, rg = h.traj_get(key)
+                assert np.array_equal(po, pg) and np.array_equal(co, cg) and (no, ro) == (ng, rg), (d, key)
+        g.close()
+        g2.close()
