@@ -667,6 +667,8 @@ int rpgo_odom_append(rpgo_handle* h, int64_t n, const uint64_t* prev_key, const 
   DeviceGuard dg(h->device);
   if (n == 0) return RPGO_OK;
   if (!prev_key || !new_key || !delta_pose || !delta_cov) return RPGO_ERR_INVALID;
+  for (int64_t k = 0; k < n; ++k) /* the all-ones key is the key table's empty marker (not a valid gtsam::Symbol) */
+    if (prev_key[k] == ~0ull || new_key[k] == ~0ull) { h->err = "rpgo_odom_append: key 0xffffffffffffffff is not supported"; return RPGO_ERR_INVALID; }
   /* A long batch is fed to the exact fold in slices (exactly what a caller appending odometry in several calls does):
    * the fold of slice i runs on the GPU while the host resolves the keys of slice i+1 and stages its factors, so the
    * wall time is the fold's own plus one slice of host work instead of the sum of both. */
