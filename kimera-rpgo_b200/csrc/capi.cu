@@ -298,6 +298,12 @@ struct rpgo_handle {
   std::map<uint64_t, int32_t> lindex; /* landmark key -> group ordinal */
 
   DevBuf d_stage;
+  /* uploads that overlap the trajectory fold: the factors of odometry slice i+1 and the closure batch travel on their own
+   * stream into their own device staging buffers while the fold of slice i runs on `stream` */
+  cudaStream_t copy_stream = nullptr;
+  DevBuf d_stage_odom[2], d_stage_lc;
+  cudaEvent_t ev_fold[2] = {nullptr, nullptr}; /* the fold that last read d_stage_odom[i] */
+  cudaEvent_t ev_lc = nullptr, ev_grow = nullptr;
   DevBuf d_lcent, d_ok, d_dist, d_scan;
   /* clique scratch: one set for the single-group entry point, one per worker of the batched one */
   CliqueSet cset;
@@ -307,11 +313,12 @@ struct rpgo_handle {
     arena.st = stream;
     scratch.st = stream;
     traj.arena = &arena;
-    for (DevBuf* b : {&d_stage, &d_lcent, &d_ok, &d_dist, &d_scan, &cset.degmask, &cset.picks, &cset.elim, &cset.result, &cset.ctl, &cset.rwork})
+    for (DevBuf* b : {&d_stage, &d_stage_odom[0], &d_stage_odom[1], &d_stage_lc, &d_lcent, &d_ok, &d_dist, &d_scan, &cset.degmask, &cset.picks, &cset.elim, &cset.result, &cset.ctl, &cset.rwork})
       b->arena = &scratch;
   }
   ~rpgo_handle() {
     DeviceGuard dg(device);
+    if (copy_stream) cudaStreamSynchronize(copy_stream);
     if (stream) cudaStreamSynchronize(stream);
     if (comm) rpgo::comm_destroy(comm);
     pin.give_back();
@@ -331,8 +338,9 @@ struct rpgo_handle {
       cudaStreamSynchronize(stream);
       cudaStreamDestroy(stream);
     }
-    for (cudaEvent_t e : ev_stage)
+    for (cudaEvent_t e : {ev_stage[0], ev_stage[1], ev_fold[0], ev_fold[1], ev_lc, ev_grow})
       if (e) cudaEventDestroy(e);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
   }
 };
 
@@ -591,7 +599,12 @@ int rpgo_create(const rpgo_cfg* cfg, rpgo_handle** out) {
   }
   h->wire();
   if (cudaEventCreateWithFlags(&h->ev_stage[0], cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_stage[1], cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&h->ev_stage[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fold[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fold[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_lc, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_grow, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
     return RPGO_ERR_CUDA;
   }
@@ -620,6 +633,7 @@ void rpgo_destroy(rpgo_handle* h) {
 int rpgo_reset(rpgo_handle* h) {
   if (!h) return RPGO_ERR_INVALID;
   DeviceGuard dg(h->device);
+  H_CHECK_CUDA(h, cudaStreamSynchronize(h->copy_stream));
   H_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
   for (CliqueWorker* w : h->workers) H_CHECK_CUDA(h, cudaStreamSynchronize(w->stream));
   for (Group* g : h->groups) delete g;
@@ -815,11 +829,27 @@ static int odom_append_batch(rpgo_handle* h, int64_t n, const uint64_t* prev_key
     }
   }
   mark("staging copy (host)");
-  H_CHECK_CUDA(h, h->d_stage.ensure(total, 0, st));
-  H_CHECK_CUDA(h, cudaMemcpyAsync(h->d_stage.p, pin, total, cudaMemcpyHostToDevice, st));
-  H_CHECK_CUDA(h, cudaEventRecord(h->ev_stage[turn], st));
+  /* exact fold: the upload goes through the copy stream into one of two device staging buffers, so that it overlaps the
+   * fold of the previous slice; `st` only waits for this slice's own upload.  (The scan path synchronises anyway.) */
+  const bool overlap = need_flush_order || h->cfg.traj_mode == RPGO_TRAJ_FOLD;
+  DevBuf& dstage = overlap ? h->d_stage_odom[turn] : h->d_stage;
+  cudaStream_t cs = overlap ? h->copy_stream : st;
+  {
+    const void* before = dstage.p;
+    H_CHECK_CUDA(h, dstage.ensure(total, 0, st));
+    if (overlap) {
+      if (dstage.p != before) { /* fresh memory is zero-filled on `st` */
+        H_CHECK_CUDA(h, cudaEventRecord(h->ev_grow, st));
+        H_CHECK_CUDA(h, cudaStreamWaitEvent(cs, h->ev_grow, 0));
+      }
+      H_CHECK_CUDA(h, cudaStreamWaitEvent(cs, h->ev_fold[turn], 0)); /* the fold that last read this buffer */
+    }
+  }
+  H_CHECK_CUDA(h, cudaMemcpyAsync(dstage.p, pin, total, cudaMemcpyHostToDevice, cs));
+  H_CHECK_CUDA(h, cudaEventRecord(h->ev_stage[turn], cs));
+  if (overlap) H_CHECK_CUDA(h, cudaStreamWaitEvent(st, h->ev_stage[turn], 0));
   mark("H2D enqueue");
-  char* d = (char*)h->d_stage.p;
+  char* d = (char*)dstage.p;
   const double* d_pose = (const double*)d;
   const double* d_cov = (const double*)(d + off_cov);
   const int32_t* d_out = (const int32_t*)(d + off_out);
@@ -869,6 +899,7 @@ static int odom_append_batch(rpgo_handle* h, int64_t n, const uint64_t* prev_key
     h->launches += 3;
   }
   H_CHECK_CUDA(h, cudaGetLastError());
+  if (overlap) H_CHECK_CUDA(h, cudaEventRecord(h->ev_fold[turn], st));
   h->traj_n = new_entries;
   /* no wait here: the H2D copy out of pin_odom and the fold keep running while the caller prepares the loop closures
    * (everything downstream is ordered on the same stream; the next rpgo_odom_append waits for ev_stage before it
@@ -964,12 +995,23 @@ int rpgo_lc_append(rpgo_handle* h, int64_t n, const uint64_t* key_from, const ui
     if (p_ib[k] == 0 && !h->key2idx.count(key_to[k])) h->missing_refs.insert(key_to[k]);
   }
   mark("stage + key lookups (host)");
-  H_CHECK_CUDA(h, h->d_stage.ensure(total, 0, st));
+  {
+    const void* before = h->d_stage_lc.p;
+    H_CHECK_CUDA(h, h->d_stage_lc.ensure(total, 0, st));
+    if (h->d_stage_lc.p != before) {
+      H_CHECK_CUDA(h, cudaEventRecord(h->ev_grow, st));
+      H_CHECK_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_grow, 0));
+    }
+  }
   H_CHECK_CUDA(h, h->d_lcent.ensure((size_t)n * E * 8, 0, st));
   H_CHECK_CUDA(h, h->d_ok.ensure((size_t)n, 0, st));
   H_CHECK_CUDA(h, h->d_dist.ensure((size_t)n * 8, 0, st));
-  H_CHECK_CUDA(h, cudaMemcpyAsync(h->d_stage.p, pin, o_dst, cudaMemcpyHostToDevice, st));
-  char* d = (char*)h->d_stage.p;
+  /* the closure batch is uploaded on the copy stream: it overlaps a trajectory fold still running on `st` (the previous
+   * user of d_stage_lc finished before the last rpgo_lc_append returned: it ends with a stream synchronisation) */
+  H_CHECK_CUDA(h, cudaMemcpyAsync(h->d_stage_lc.p, pin, o_dst, cudaMemcpyHostToDevice, h->copy_stream));
+  H_CHECK_CUDA(h, cudaEventRecord(h->ev_lc, h->copy_stream));
+  H_CHECK_CUDA(h, cudaStreamWaitEvent(st, h->ev_lc, 0));
+  char* d = (char*)h->d_stage_lc.p;
   launch_lc_prepare(h->dim, h->mode, (int)n, (const double*)d, (const double*)(d + o_cov), (const int32_t*)(d + o_if),
                     (const int32_t*)(d + o_ib), (const uint8_t*)(d + o_ck), h->traj.as<double>(), h->th,
                     h->d_lcent.as<double>(), h->d_ok.as<uint8_t>(), h->d_dist.as<double>(), st);
