@@ -50,142 +50,8 @@ __global__ void traj_fold_kernel(int n_chains, const FoldChain* __restrict__ cha
 }
 
 
-/* K1, warp-cooperative exact fold (MODE_PCM): the strict left fold of the reference, with the covariance
- * rows of H S H^T + S_delta spread over N lanes (lane r owns row r).  Every product is accumulated in
- * exactly the order hsht() uses, so the result is bit-identical to the one-thread fold; only the critical
- * path shrinks (~6x fewer dependent FP64 operations per step, rows exchanged with shuffles). */
-template <int D>
-__global__ void __launch_bounds__(32) traj_fold_warp_kernel(int n_chains, const FoldChain* __restrict__ chains,
-                                                            const int32_t* __restrict__ out_idx, const double* __restrict__ dpose,
-                                                            const double* __restrict__ dcov, double* entries) {
-  constexpr int E = Dim<D>::ENTRY, PS = Dim<D>::PS, N = Dim<D>::N, NN = N * N, OC = Dim<D>::OFF_COV, RD = Dim<D>::RD,
-                TD = Dim<D>::TD;
-  const int c = blockIdx.x;
-  if (c >= n_chains) return;
-  const int lane = threadIdx.x;
-  const int r = lane < N ? lane : 0; /* row owned by this lane (lanes >= N shadow row 0 and never store) */
-  const FoldChain ch = chains[c];
-  Pose<D> P;
-  load_pose<D>(entries + (size_t)ch.start_idx * E, 1, P);
-  double S[N]; /* row r of the running covariance */
-#pragma unroll
-  for (int j = 0; j < N; ++j) S[j] = entries[(size_t)ch.start_idx * E + OC + r * N + j];
-  bool rot = entries[(size_t)ch.start_idx * E + Dim<D>::OFF_ROT] != 0.0;
-  /* software prefetch: the factor of step s+1 is loaded while step s computes (the loads do not depend on
-   * the running value, only the arithmetic does) */
-  Pose<D> nDl;
-  double nDiag[RD], nRow[N];
-  int nOut = 0;
-  auto fetch = [&](int k) {
-    const double* dp = dpose + (size_t)k * PS;
-    const double* dc = dcov + (size_t)k * NN;
-#pragma unroll
-    for (int i = 0; i < PS; ++i) nDl.m[i] = dp[i];
-#pragma unroll
-    for (int i = 0; i < RD; ++i) nDiag[i] = dc[i * N + i];
-#pragma unroll
-    for (int j = 0; j < N; ++j) nRow[j] = dc[r * N + j];
-    nOut = out_idx[k];
-  };
-  if (ch.n_steps > 0) fetch(ch.first_step);
-  for (int s = 0; s < ch.n_steps; ++s) {
-    const Pose<D> Dl = nDl;
-    double diag[RD], row[N];
-#pragma unroll
-    for (int i = 0; i < RD; ++i) diag[i] = nDiag[i];
-#pragma unroll
-    for (int j = 0; j < N; ++j) row[j] = nRow[j];
-    const int cur_out = nOut;
-    if (s + 1 < ch.n_steps) fetch(ch.first_step + s + 1);
-    /* from_factor: NaN rotation covariance => keep only the translation block (GeometryUtils.h:98-113) */
-    double tr = diag[0];
-#pragma unroll
-    for (int i = 1; i < RD; ++i) tr = tr + diag[i];
-    const bool drot = !(tr != tr);
-    double Dc[N];
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-      double v = row[j];
-      if (!drot) v = (r >= RD && j >= RD && r < RD + TD && j < RD + TD) ? v : 0.0;
-      Dc[j] = v;
-    }
-    const Adj<D> H = adjoint<D>(inverse<D>(Dl));
-    /* T1 row r = H[r,:] * S  (rows of S come from the owning lanes) */
-    double t[N];
-    if (D == 3) {
-      const double* A = H.h;
-      const double* B = H.h + 9;
-      double Sk[3][N];
-#pragma unroll
-      for (int kk = 0; kk < 3; ++kk)
-#pragma unroll
-        for (int j = 0; j < N; ++j) Sk[kk][j] = __shfl_sync(0xffffffffu, S[j], kk);
-      /* row selection by value selects (a lane-dependent index would put H into local memory) */
-      double h0 = A[0], h1 = A[1], h2 = A[2], a0 = A[0], a1 = A[1], a2 = A[2];
-#pragma unroll
-      for (int i = 1; i < 6; ++i) {
-        const double* src = i < 3 ? A + i * 3 : B + (i - 3) * 3;
-        const bool sel = (r == i);
-        h0 = sel ? src[0] : h0; h1 = sel ? src[1] : h1; h2 = sel ? src[2] : h2;
-        const double* asrc = A + (i < 3 ? i : i - 3) * 3;
-        a0 = sel ? asrc[0] : a0; a1 = sel ? asrc[1] : a1; a2 = sel ? asrc[2] : a2;
-      }
-      const double arow[3] = {a0, a1, a2};
-#pragma unroll
-      for (int j = 0; j < N; ++j) t[j] = dot3(h0, h1, h2, Sk[0][j], Sk[1][j], Sk[2][j]);
-#pragma unroll
-      for (int kk = 3; kk < 6; ++kk) {
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-          const double sv = __shfl_sync(0xffffffffu, S[j], kk);
-          if (r >= 3) t[j] = fma(arow[kk - 3], sv, t[j]);
-        }
-      }
-      /* out row r = t * H^T + Dc */
-#pragma unroll
-      for (int j = 0; j < 3; ++j) S[j] = dot3(t[0], t[1], t[2], A[j * 3], A[j * 3 + 1], A[j * 3 + 2]) + Dc[j];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        double acc = dot3(t[0], t[1], t[2], B[j * 3], B[j * 3 + 1], B[j * 3 + 2]);
-        acc = fma(t[3], A[j * 3], acc);
-        acc = fma(t[4], A[j * 3 + 1], acc);
-        acc = fma(t[5], A[j * 3 + 2], acc);
-        S[3 + j] = acc + Dc[3 + j];
-      }
-    } else {
-      double Sk[3][N];
-#pragma unroll
-      for (int kk = 0; kk < 3; ++kk)
-#pragma unroll
-        for (int j = 0; j < N; ++j) Sk[kk][j] = __shfl_sync(0xffffffffu, S[j], kk);
-      double g0 = H.h[0], g1 = H.h[1], g2 = H.h[2];
-#pragma unroll
-      for (int i = 1; i < 3; ++i) {
-        const bool sel = (r == i);
-        g0 = sel ? H.h[i * 3] : g0; g1 = sel ? H.h[i * 3 + 1] : g1; g2 = sel ? H.h[i * 3 + 2] : g2;
-      }
-#pragma unroll
-      for (int j = 0; j < N; ++j) t[j] = dot3(g0, g1, g2, Sk[0][j], Sk[1][j], Sk[2][j]);
-#pragma unroll
-      for (int j = 0; j < N; ++j) S[j] = dot3(t[0], t[1], t[2], H.h[j * 3], H.h[j * 3 + 1], H.h[j * 3 + 2]) + Dc[j];
-    }
-    P = compose<D>(P, Dl);
-    rot = rot && drot;
-    double* o = entries + (size_t)cur_out * E;
-    if (lane < N) {
-#pragma unroll
-      for (int j = 0; j < N; ++j) o[OC + r * N + j] = S[j];
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int i = 0; i < PS; ++i) o[i] = P.m[i];
-      o[Dim<D>::OFF_ROT] = rot ? 1.0 : 0.0;
-      o[Dim<D>::OFF_NODE] = 0.0;
-    }
-  }
-}
-
-/* K1, batched exact fold (MODE_PCM, default).  Same arithmetic, same order as the kernel above (bit-identical), but
+/* K1, batched exact fold (MODE_PCM; round 1's kernel, kept as the A/B reference: RPGO_FOLD_V2=1).  Same arithmetic, same
+ * order as the one-thread fold above (bit-identical), but
  * everything that does not depend on the running value is taken off the sequential path:
  *   - the factors of the next 32 steps are copied global -> shared asynchronously (cp.async) while the current 32
  *     steps are folded, so the chain never waits on HBM;
@@ -369,13 +235,10 @@ __global__ void __launch_bounds__(64) traj_fold_batched_kernel(int n_chains, con
  *     the chain warps fold block b (the batched kernel prepared a block between two chain phases);
  *   - the chain warps read the delta covariance / pose / output slot straight from the raw slot (the NaN mask of
  *     from_factor is one select per element) and fetch the operands of step i+1 before the dependent part of step i;
- *   - RPGO_FOLD_XCHG selects how the covariance is exchanged between the two products of H S H^T:
- *       0  shuffles (18 + 18 SHFL per step, as in the batched kernel)
- *       1  two shared-memory hops: S column-major (a lane reads its two columns with 6 LDS.128), H S row-major
- *       2  one hop: every lane reads the whole S and recomputes the row of H S it needs. */
-#ifndef RPGO_FOLD_XCHG
-#define RPGO_FOLD_XCHG 1
-#endif
+ *   - the two products of H S H^T exchange the covariance through two shared-memory hops: S column-major (a lane reads
+ *     its two columns with 6 LDS.128), H S row-major.  Measured alternatives (profiles/r2_k3_variants.md): shuffles
+ *     (18 + 18 SHFL per step) and a single hop where every lane reads the whole S and recomputes its row of H S -- both
+ *     within 2 % of this form. */
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -546,14 +409,10 @@ __global__ void __launch_bounds__(96) traj_fold_pipelined_kernel(int n_chains, c
     const bool lower = (D == 3) && r >= 3;
     const uint32_t a_xs = opaque_u32((uint32_t)__cvta_generic_to_shared(&xs[0]));
     const uint32_t a_xt = opaque_u32((uint32_t)__cvta_generic_to_shared(&xt[0]));
-#if RPGO_FOLD_XCHG == 2
-    const uint32_t w_xs = a_xs + (r * N + cg) * 8; /* row-major S */
-#else
     const uint32_t w_xs = a_xs + (cg * N + r) * 8; /* column-major S: element (r, cg); (r, cg + 3) is 3 N doubles further */
     const uint32_t r_xs = a_xs + cg * N * 8;
     const uint32_t w_xt = a_xt + (r * N + cg) * 8; /* row-major H S */
     const uint32_t r_xt = a_xt + r * N * 8;
-#endif
     double* const obase = entries + OC + r * N + cg;
     for (int b = 0; b < nb; ++b) {
       const int slot = b % 3, st = b & 1;
@@ -588,29 +447,6 @@ __global__ void __launch_bounds__(96) traj_fold_pipelined_kernel(int n_chains, c
         for (int cc = 0; cc < CPL; ++cc) dc[cc] = ndc[cc];
         double* o = no;
         double tf[N];
-#if RPGO_FOLD_XCHG == 2
-        /* one hop: S row-major in shared memory, every lane recomputes row r of H S */
-#pragma unroll
-        for (int cc = 0; cc < CPL; ++cc) sts_f64(w_xs + 3 * cc * 8, S[cc]);
-        __syncwarp();
-        double sa[NN + 1];
-#pragma unroll
-        for (int q = 0; q < NN - 1; q += 2) lds_f64x2(a_xs + q * 8, sa[q], sa[q + 1]);
-        if (NN & 1) sa[NN - 1] = lds_f64(a_xs + (NN - 1) * 8);
-        fetch(min(i + 1, cnt - 1));
-#pragma unroll
-        for (int k = 0; k < N; ++k) {
-          double t = dot3(h[0], h[1], h[2], sa[k], sa[N + k], sa[2 * N + k]);
-          if (D == 3) {
-            double t6 = fma(a[0], sa[(3 * N + k) % NN], t);
-            t6 = fma(a[1], sa[(4 * N + k) % NN], t6);
-            t6 = fma(a[2], sa[(5 * N + k) % NN], t6);
-            t = sel_f64(lower, t6, t);
-          }
-          tf[k] = t;
-        }
-        __syncwarp(); /* all reads of xs done before the next step overwrites it */
-#else
         double t[CPL];
         /* hop 1: S column-major; a lane reads its own columns */
 #pragma unroll
@@ -650,7 +486,6 @@ __global__ void __launch_bounds__(96) traj_fold_pipelined_kernel(int n_chains, c
 #pragma unroll
           for (int j = 0; j < N; ++j) tf[j] = lds_f64(r_xt + j * 8);
         }
-#endif
         /* out(r, j) = (H S)(r, :) . H(j, :) + Dc(r, j) */
         S[0] = dot3(tf[0], tf[1], tf[2], A[0], A[1], A[2]) + dc[0];
         if (D == 3) {
@@ -674,11 +509,7 @@ void launch_traj_fold(int dim, int mode, int n_chains, const FoldChain* chains, 
   /* one chain per block so that independent robots land on different SMs */
   const int blocks = n_chains;
   if (mode == MODE_PCM) {
-    static const bool v1 = getenv("RPGO_FOLD_V1") != nullptr; /* A/B knob: the one-warp kernel */
-    if (v1) {
-      if (dim == 3) traj_fold_warp_kernel<3><<<blocks, 32, 0, st>>>(n_chains, chains, out_idx, delta_pose, delta_cov, entries);
-      else traj_fold_warp_kernel<2><<<blocks, 32, 0, st>>>(n_chains, chains, out_idx, delta_pose, delta_cov, entries);
-    } else {
+    {
       static const bool v2 = getenv("RPGO_FOLD_V2") != nullptr; /* A/B knob: the two-warp batched kernel */
       if (v2) {
         if (dim == 3) traj_fold_batched_kernel<3><<<blocks, 64, 0, st>>>(n_chains, chains, out_idx, delta_pose, delta_cov, entries);

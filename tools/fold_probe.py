@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """K1 probe: odom_append (+ sync) wall time for 2D / 3D chains and a checksum of sampled trajectory entries, so that kernel
-variants (RPGO_LIB_PATH, RPGO_FOLD_V2=1 = the two-warp batched kernel, RPGO_FOLD_V1=1 = the one-warp kernel) can be compared
+variants (RPGO_LIB_PATH, RPGO_FOLD_V2=1 = the two-warp batched kernel) can be compared
 bit for bit.  Run under gpurun."""
 import hashlib, importlib, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
