@@ -94,6 +94,11 @@ class IdList:
     def __eq__(self, other):
         return list(self) == list(other)
 
+    def __array__(self, dtype=None, copy=None):
+        parts = [np.asarray(self._l, dtype=np.int64)] + [np.asarray(c, dtype=np.int64) for c in self._chunks]
+        a = np.concatenate(parts) if len(parts) > 1 else parts[0]
+        return a if dtype is None else a.astype(dtype, copy=False)
+
     def __repr__(self):
         return "IdList(%r)" % (self._flush(),)
 

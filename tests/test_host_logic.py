@@ -35,6 +35,11 @@ def test_idlist_behaves_like_a_list():
     x.extend(np.arange(5)); ref.extend(range(5))
     assert x.pop() == ref.pop() and len(x) == len(ref) and x[len(ref) - 1] == ref[-1]
     assert all(isinstance(v, int) for v in x) and list(x) == ref
+    y = IdList([9, 8])
+    y.extend(np.arange(3, dtype=np.int32))
+    y.extend(range(20, 22))
+    assert np.array(y, dtype=np.int64).tolist() == [9, 8, 0, 1, 2, 20, 21] and np.asarray(y).dtype == np.int64
+    assert len(y) == 7 and y[2] == 0  # conversion does not consume the chunks
     try:
         IdList(range(2))[5]
         assert False
