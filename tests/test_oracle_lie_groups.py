@@ -129,3 +129,20 @@ def test_inverse_keeps_the_covariance_and_mahalanobis_is_the_quadratic_form(d):
         lg = vee(d, np.real(logm(mat(d, a))))
         want = np.sqrt(lg @ np.linalg.inv(ca) @ lg)          # GeometryUtils.h:172-186
         assert np.isclose(orc.pwc_mahalanobis(d, (a, ca, 1)), want, rtol=1e-9)
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_pose_with_node_norms_take_head_and_tail_of_the_log_vector(d):
+    """GeometryUtils.h:275-288: avg_trans_norm = |log.tail(t_dim)| / node, avg_rot_norm = |log.head(r_dim)| / node, literally:
+    for Pose2 (Logmap order x, y, theta; r_dim = 1, t_dim = 2) the 'translation' norm is |(y, theta)| and the 'rotation' norm
+    is |x| -- the reference's own quirk, which the oracle and the kernels reproduce"""
+    rng = np.random.default_rng(600 + d)
+    r_dim, t_dim = (1, 2) if d == 2 else (3, 3)
+    for _ in range(100):
+        p = rand_pose(d, rng)
+        node = int(rng.integers(1, 40))
+        lg = vee(d, np.real(logm(mat(d, p))))
+        tr, ro = orc.pwn_norms(d, p, node)
+        assert np.isclose(tr, np.linalg.norm(lg[-t_dim:]) / node, rtol=1e-9, atol=1e-12)
+        assert np.isclose(ro, np.linalg.norm(lg[:r_dim]) / node, rtol=1e-9, atol=1e-12)
+    assert orc.pwn_norms(d, rand_pose(d, rng), 3, rot=0)[1] == 0.0   # rotation_info = false: avg_rot_norm returns 0
