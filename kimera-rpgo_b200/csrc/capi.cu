@@ -93,7 +93,6 @@ struct Arena {
       cudaGetLastError();
       return nullptr;
     }
-    /* keep the partially used previous chunk reachable for small requests: put the big one first */
     chunks.push_back(Chunk{(char*)p, cap, bytes});
     return p;
   }
@@ -205,7 +204,12 @@ static void staged_copy(void* dst, const void* src, size_t bytes) {
   for (size_t t = 1; t < T; ++t) {
     const size_t off = t * per;
     if (off >= bytes) break;
-    th.emplace_back([=]() { memcpy((char*)dst + off, (const char*)src + off, std::min(per, bytes - off)); });
+    const size_t len = std::min(per, bytes - off);
+    try {
+      th.emplace_back([=]() { memcpy((char*)dst + off, (const char*)src + off, len); });
+    } catch (...) { /* no thread to be had (resource limits of the host application): copy this part inline */
+      memcpy((char*)dst + off, (const char*)src + off, len);
+    }
   }
   memcpy(dst, src, std::min(per, bytes));
   for (auto& x : th) x.join();
